@@ -473,7 +473,7 @@ int ref_ew_pointsource_error( void* h, double t, double** u_per_grid, double* ou
       Uex[g].define(3,ew->m_iStart[g],ew->m_iEnd[g],ew->m_jStart[g],ew->m_jEnd[g],ew->m_kStart[g],ew->m_kEnd[g]);
       Ucmp[g].define(3,ew->m_iStart[g],ew->m_iEnd[g],ew->m_jStart[g],ew->m_jEnd[g],ew->m_kStart[g],ew->m_kEnd[g]);
       Uex[g].set_value(0.0);
-      memcpy( Ucmp[g].c_ptr(), u_per_grid[g], sizeof(double)*3*Ucmp[g].m_npts );
+      memcpy( Ucmp[g].c_ptr(), u_per_grid[g], sizeof(double)*Ucmp[g].m_npts ); // m_npts counts all components
    }
    ew->exactSol( t, Uex, ew->m_globalUniqueSources );
    float_sw4 errInf=0, errL2=0, solInf=0;

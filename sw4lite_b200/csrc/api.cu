@@ -1,0 +1,716 @@
+// extern "C" layer of libsw4b200.so (declared in include/sw4b200.h).
+#include "common.cuh"
+#include "sbp4_tables.h"
+#include "../../include/sw4b200.h"
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <map>
+
+namespace sw4b200 {
+
+static thread_local char g_err[1024] = "";
+static int g_launches = 0;
+static cudaStream_t g_streams[4] = { 0, 0, 0, 0 };
+static bool g_init = false;
+static int g_device = -1;
+
+int set_error( const char* fmt, ... )
+{
+   va_list ap;
+   va_start( ap, fmt );
+   vsnprintf( g_err, sizeof( g_err ), fmt, ap );
+   va_end( ap );
+   return 1;
+}
+int check_launch( const char* what )
+{
+   cudaError_t e = cudaGetLastError();
+   if( e != cudaSuccess ) return set_error( "%s: %s", what, cudaGetErrorString( e ) );
+   return 0;
+}
+void count_launch( int n ) { g_launches += n; }
+cudaStream_t as_stream( void* s ) { return s ? (cudaStream_t)s : g_streams[0]; }
+
+#define CUDA_OK( call )                                                                          \
+   do                                                                                            \
+   {                                                                                             \
+      cudaError_t e_ = ( call );                                                                 \
+      if( e_ != cudaSuccess ) return set_error( "%s: %s", #call, cudaGetErrorString( e_ ) );     \
+   } while( 0 )
+
+static int need_init()
+{
+   if( !g_init ) return set_error( "sw4b200_init has not been called (no CUDA device selected; there is no CPU path)" );
+   return 0;
+}
+
+static void builtin_coefficients( double* acof, double* ghcof, double* bope, double* sbop )
+{
+   for( int n = 0; n < 384; n++ ) acof[n] = 0;
+   for( int n = 0; n < 48; n++ ) bope[n] = 0;
+   for( int n = 0; n < 6; n++ ) ghcof[n] = 0;
+   for( size_t n = 0; n < sizeof( SW4B200_ACOF_NZ ) / sizeof( SW4B200_ACOF_NZ[0] ); n++ )
+      acof[SW4B200_ACOF_NZ[n].idx] = SW4B200_ACOF_NZ[n].num / SW4B200_ACOF_NZ[n].den;
+   for( size_t n = 0; n < sizeof( SW4B200_BOPE_NZ ) / sizeof( SW4B200_BOPE_NZ[0] ); n++ )
+      bope[SW4B200_BOPE_NZ[n].idx] = SW4B200_BOPE_NZ[n].num / SW4B200_BOPE_NZ[n].den;
+   for( size_t n = 0; n < sizeof( SW4B200_GHCOF_NZ ) / sizeof( SW4B200_GHCOF_NZ[0] ); n++ )
+      ghcof[SW4B200_GHCOF_NZ[n].idx] = SW4B200_GHCOF_NZ[n].num / SW4B200_GHCOF_NZ[n].den;
+   for( int n = 0; n < 5; n++ ) sbop[n] = SW4B200_SBOP[n].num / SW4B200_SBOP[n].den;
+}
+
+static bool use_fast_path()
+{
+   static int v = -1;
+   if( v < 0 )
+   {
+      const char* e = getenv( "SW4B200_FORCE_V1" );
+      v = ( e && e[0] == '1' ) ? 0 : 1;
+   }
+   return v == 1;
+}
+
+// one fused pass over a block: interior rows (fast SoA kernel when possible), closure rows and shell
+static int run_rhs( RhsMode mode, const RhsArgs& a, int corder, cudaStream_t st )
+{
+   int rc;
+   if( corder && use_fast_path() )
+      rc = launch_rhs_fast( mode, a, st );
+   else
+      rc = launch_rhs_v1( mode, a, st );
+   if( rc ) return rc;
+   if( mode != MODE_LU ) rc = launch_shell_update( mode, a, st );
+   return rc;
+}
+
+} // namespace sw4b200
+
+using namespace sw4b200;
+
+struct sw4b200_grid
+{
+   sw4b200_grid_desc d;
+   Block b;
+   cudaStream_t st;
+   double *U, *Um, *Up, *Up2;
+   double *mu, *la, *rho, *jac, *met;
+   double *str[3], *dc[3], *co[3];
+   double* bforce[6];
+   size_t nbf[6];
+   int nsrc;
+   long long* d_srcidx;
+   double *d_f, *h_f;
+   int nrec;
+   long long* d_recidx;
+   double *d_rec, *h_rec;
+   double* halo_buf[2];
+};
+
+extern "C" {
+
+int sw4b200_init( int device )
+{
+   int n = 0;
+   cudaError_t e = cudaGetDeviceCount( &n );
+   if( e != cudaSuccess || n == 0 )
+      return set_error( "sw4b200_init: no CUDA device (%s); this library has no CPU fallback",
+			e != cudaSuccess ? cudaGetErrorString( e ) : "device count 0" );
+   if( device < 0 || device >= n ) return set_error( "sw4b200_init: device %d out of range [0,%d)", device, n );
+   CUDA_OK( cudaSetDevice( device ) );
+   if( g_init && g_device == device ) return 0;
+   cudaDeviceProp prop;
+   CUDA_OK( cudaGetDeviceProperties( &prop, device ) );
+   if( prop.major < 10 )
+      return set_error( "sw4b200_init: device %d is sm_%d%d; this library is built for sm_100a only", device,
+			prop.major, prop.minor );
+   for( int s = 0; s < 4; s++ ) CUDA_OK( cudaStreamCreateWithFlags( &g_streams[s], cudaStreamNonBlocking ) );
+   g_device = device;
+   g_init = true;
+   double acof[384], ghcof[6], bope[48], sbop[5];
+   builtin_coefficients( acof, ghcof, bope, sbop );
+   return sw4b200_copy_stencilcoefficients( acof, ghcof, bope, sbop );
+}
+
+int sw4b200_finalize( void )
+{
+   if( !g_init ) return 0;
+   cudaDeviceSynchronize();
+   for( int s = 0; s < 4; s++ )
+      if( g_streams[s] ) { cudaStreamDestroy( g_streams[s] ); g_streams[s] = 0; }
+   g_init = false;
+   return 0;
+}
+
+int sw4b200_device_count( void )
+{
+   int n = 0;
+   if( cudaGetDeviceCount( &n ) != cudaSuccess ) { cudaGetLastError(); return 0; }
+   return n;
+}
+const char* sw4b200_last_error( void ) { return g_err; }
+const char* sw4b200_version( void ) { return "sw4b200 0.1 (sm_100a)"; }
+void* sw4b200_stream( int st ) { return ( st >= 0 && st < 4 ) ? (void*)g_streams[st] : 0; }
+int sw4b200_sync_stream( int st )
+{
+   if( need_init() ) return 1;
+   if( st < 0 || st >= 4 ) return set_error( "sync_stream: bad stream %d", st );
+   CUDA_OK( cudaStreamSynchronize( g_streams[st] ) );
+   return 0;
+}
+int sw4b200_sync_device( void )
+{
+   if( need_init() ) return 1;
+   CUDA_OK( cudaDeviceSynchronize() );
+   return 0;
+}
+int sw4b200_kernel_launch_count( void ) { return g_launches; }
+
+void* sw4b200_malloc( size_t bytes )
+{
+   if( need_init() ) return 0;
+   void* p = 0;
+   cudaError_t e = cudaMalloc( &p, bytes ? bytes : 8 );
+   if( e != cudaSuccess ) { set_error( "cudaMalloc(%zu): %s", bytes, cudaGetErrorString( e ) ); return 0; }
+   return p;
+}
+int sw4b200_free( void* p ) { if( p ) CUDA_OK( cudaFree( p ) ); return 0; }
+void* sw4b200_malloc_host( size_t bytes )
+{
+   if( need_init() ) return 0;
+   void* p = 0;
+   cudaError_t e = cudaMallocHost( &p, bytes ? bytes : 8 );
+   if( e != cudaSuccess ) { set_error( "cudaMallocHost(%zu): %s", bytes, cudaGetErrorString( e ) ); return 0; }
+   return p;
+}
+int sw4b200_free_host( void* p ) { if( p ) CUDA_OK( cudaFreeHost( p ) ); return 0; }
+int sw4b200_memcpy_h2d( void* d, const void* h, size_t bytes, void* stream )
+{
+   if( need_init() ) return 1;
+   CUDA_OK( cudaMemcpyAsync( d, h, bytes, cudaMemcpyHostToDevice, as_stream( stream ) ) );
+   return 0;
+}
+int sw4b200_memcpy_d2h( void* h, const void* d, size_t bytes, void* stream )
+{
+   if( need_init() ) return 1;
+   CUDA_OK( cudaMemcpyAsync( h, d, bytes, cudaMemcpyDeviceToHost, as_stream( stream ) ) );
+   return 0;
+}
+int sw4b200_memcpy_d2d( void* dd, const void* ds, size_t bytes, void* stream )
+{
+   if( need_init() ) return 1;
+   CUDA_OK( cudaMemcpyAsync( dd, ds, bytes, cudaMemcpyDeviceToDevice, as_stream( stream ) ) );
+   return 0;
+}
+int sw4b200_memset_zero( void* d, size_t bytes, void* stream )
+{
+   if( need_init() ) return 1;
+   CUDA_OK( cudaMemsetAsync( d, 0, bytes, as_stream( stream ) ) );
+   return 0;
+}
+
+int sw4b200_get_stencil_coefficients( double* acof, double* ghcof, double* bope, double* sbop )
+{
+   builtin_coefficients( acof, ghcof, bope, sbop );
+   return 0;
+}
+int sw4b200_copy_stencilcoefficients( const double* acof, const double* ghcof, const double* bope, const double* sbop )
+{
+   if( need_init() ) return 1;
+   CUDA_OK( cudaMemcpyToSymbol( c_acof, acof, 384 * sizeof( double ) ) );
+   CUDA_OK( cudaMemcpyToSymbol( c_ghcof, ghcof, 6 * sizeof( double ) ) );
+   CUDA_OK( cudaMemcpyToSymbol( c_bope, bope, 48 * sizeof( double ) ) );
+   CUDA_OK( cudaMemcpyToSymbol( c_sbop, sbop, 5 * sizeof( double ) ) );
+   return 0;
+}
+
+static int check_bounds( int ifirst, int ilast, int jfirst, int jlast, int kfirst, int klast )
+{
+   if( ilast - ifirst + 1 < 5 || jlast - jfirst + 1 < 5 || klast - kfirst + 1 < 5 )
+      return set_error( "block %d:%d x %d:%d x %d:%d is smaller than the 5-point stencil", ifirst, ilast, jfirst,
+			jlast, kfirst, klast );
+   return 0;
+}
+
+int sw4b200_rhs4sg( int corder, int ifirst, int ilast, int jfirst, int jlast, int kfirst, int klast, int nk,
+		    const int* onesided, double* lu, const double* u, const double* mu, const double* la, double h,
+		    const double* strx, const double* stry, const double* strz, void* stream )
+{
+   if( need_init() || check_bounds( ifirst, ilast, jfirst, jlast, kfirst, klast ) ) return 1;
+   RhsArgs a;
+   memset( &a, 0, sizeof( a ) );
+   a.b = make_block( corder, ifirst, ilast, jfirst, jlast, kfirst, klast );
+   a.nk = nk; a.onesided4 = onesided[4] == 1; a.onesided5 = onesided[5] == 1;
+   a.out = lu; a.u = u; a.mu = mu; a.la = la; a.strx = strx; a.stry = stry; a.strz = strz; a.h = h; a.dt = 1;
+   return run_rhs( MODE_LU, a, corder, as_stream( stream ) );
+}
+
+int sw4b200_rhs4_pred( int corder, int ifirst, int ilast, int jfirst, int jlast, int kfirst, int klast, int nk,
+		       const int* onesided, double* up, const double* u, const double* um, const double* mu,
+		       const double* la, const double* rho, const double* fo, const double* strx,
+		       const double* stry, const double* strz, double h, double dt, void* stream )
+{
+   if( need_init() || check_bounds( ifirst, ilast, jfirst, jlast, kfirst, klast ) ) return 1;
+   RhsArgs a;
+   memset( &a, 0, sizeof( a ) );
+   a.b = make_block( corder, ifirst, ilast, jfirst, jlast, kfirst, klast );
+   a.nk = nk; a.onesided4 = onesided[4] == 1; a.onesided5 = onesided[5] == 1;
+   a.out = up; a.u = u; a.um = um; a.mu = mu; a.la = la; a.rho = rho; a.fo = fo;
+   a.strx = strx; a.stry = stry; a.strz = strz; a.h = h; a.dt = dt;
+   return run_rhs( MODE_PRED, a, corder, as_stream( stream ) );
+}
+
+int sw4b200_rhs4_corr( int corder, int ifirst, int ilast, int jfirst, int jlast, int kfirst, int klast, int nk,
+		       const int* onesided, double* up_out, const double* up, const double* u, const double* um,
+		       const double* mu, const double* la, const double* rho, const double* fo,
+		       const double* strx, const double* stry, const double* strz, const double* dcx,
+		       const double* dcy, const double* dcz, const double* cox, const double* coy,
+		       const double* coz, double beta, int sg_order, double h, double dt, void* stream )
+{
+   if( need_init() || check_bounds( ifirst, ilast, jfirst, jlast, kfirst, klast ) ) return 1;
+   if( up_out == up ) return set_error( "rhs4_corr: up_out must not alias up (the corrector reads up with a 2-point halo)" );
+   if( sg_order != 0 && sg_order != 4 && sg_order != 6 ) return set_error( "rhs4_corr: sg_order must be 0, 4 or 6" );
+   RhsArgs a;
+   memset( &a, 0, sizeof( a ) );
+   a.b = make_block( corder, ifirst, ilast, jfirst, jlast, kfirst, klast );
+   a.nk = nk; a.onesided4 = onesided[4] == 1; a.onesided5 = onesided[5] == 1;
+   a.out = up_out; a.up = up; a.u = u; a.um = um; a.mu = mu; a.la = la; a.rho = rho; a.fo = fo;
+   a.strx = strx; a.stry = stry; a.strz = strz; a.h = h; a.dt = dt;
+   a.dcx = dcx; a.dcy = dcy; a.dcz = dcz; a.cox = cox; a.coy = coy; a.coz = coz; a.beta = beta;
+   a.sg_order = beta == 0 ? 0 : sg_order;
+   return run_rhs( MODE_CORR, a, corder, as_stream( stream ) );
+}
+
+int sw4b200_predfort( int corder, int ib, int ie, int jb, int je, int kb, int ke, double* up, const double* u,
+		      const double* um, const double* lu, const double* fo, const double* rho, double dt2, void* stream )
+{
+   if( need_init() ) return 1;
+   return launch_predfort( make_block( corder, ib, ie, jb, je, kb, ke ), up, u, um, lu, fo, rho, dt2, as_stream( stream ) );
+}
+int sw4b200_corrfort( int corder, int ib, int ie, int jb, int je, int kb, int ke, double* up, const double* lu,
+		      const double* fo, const double* rho, double dt4, void* stream )
+{
+   if( need_init() ) return 1;
+   return launch_corrfort( make_block( corder, ib, ie, jb, je, kb, ke ), up, lu, fo, rho, dt4, as_stream( stream ) );
+}
+int sw4b200_dpdmtfort( int ib, int ie, int jb, int je, int kb, int ke, const double* up, const double* u,
+		       const double* um, double* u2, double dt2i, void* stream )
+{
+   if( need_init() ) return 1;
+   const long long n = 3LL * ( ie - ib + 1 ) * ( je - jb + 1 ) * ( ke - kb + 1 );
+   return launch_dpdmt( n, up, u, um, u2, dt2i, as_stream( stream ) );
+}
+int sw4b200_addsgd( int corder, int order, int ifirst, int ilast, int jfirst, int jlast, int kfirst, int klast,
+		    double* up, const double* u, const double* um, const double* rho, const double* dcx,
+		    const double* dcy, const double* dcz, const double* strx, const double* stry,
+		    const double* strz, const double* cox, const double* coy, const double* coz, double beta,
+		    void* stream )
+{
+   if( need_init() ) return 1;
+   if( order != 4 && order != 6 ) return set_error( "addsgd: order must be 4 or 6" );
+   return launch_addsgd( order, make_block( corder, ifirst, ilast, jfirst, jlast, kfirst, klast ), up, u, um, rho,
+			 dcx, dcy, dcz, strx, stry, strz, cox, coy, coz, beta, as_stream( stream ) );
+}
+int sw4b200_bcfortsg( int corder, int ib, int ie, int jb, int je, int kb, int ke, const int* wind, int nx, int ny,
+		      int nz, double* u, double h, const int* bccnd, const double* mu, const double* la,
+		      const double* const* bforce, const double* strx, const double* stry, void* stream )
+{
+   if( need_init() ) return 1;
+   Int36 w; Int6 bc; Ptr6 bf;
+   for( int s = 0; s < 36; s++ ) w.v[s] = wind[s];
+   for( int s = 0; s < 6; s++ ) { bc.v[s] = bccnd[s]; bf.p[s] = bforce ? bforce[s] : 0; }
+   return launch_bcfortsg( make_block( corder, ib, ie, jb, je, kb, ke ), w, nx, ny, nz, u, h, bc, mu, la, bf, strx,
+			   stry, as_stream( stream ) );
+}
+
+int sw4b200_rhs4sgcurv( int corder, int ifirst, int ilast, int jfirst, int jlast, int kfirst, int klast,
+			const double* u, const double* mu, const double* la, const double* met, const double* jac,
+			double* lu, const int* onesided, const double* strx, const double* stry, void* stream )
+{
+   if( need_init() || check_bounds( ifirst, ilast, jfirst, jlast, kfirst, klast ) ) return 1;
+   return launch_rhs4sgcurv( make_block( corder, ifirst, ilast, jfirst, jlast, kfirst, klast ), u, mu, la, met, jac,
+			     lu, onesided[4] == 1, strx, stry, as_stream( stream ) );
+}
+int sw4b200_addsgdc( int corder, int order, int ifirst, int ilast, int jfirst, int jlast, int kfirst, int klast,
+		     double* up, const double* u, const double* um, const double* rho, const double* dcx,
+		     const double* dcy, const double* strx, const double* stry, const double* jac,
+		     const double* cox, const double* coy, double beta, void* stream )
+{
+   if( need_init() ) return 1;
+   if( order != 4 && order != 6 ) return set_error( "addsgdc: order must be 4 or 6" );
+   return launch_addsgdc( order, make_block( corder, ifirst, ilast, jfirst, jlast, kfirst, klast ), up, u, um, rho,
+			  dcx, dcy, strx, stry, jac, cox, coy, beta, as_stream( stream ) );
+}
+int sw4b200_freesurfcurvisg( int corder, int ib, int ie, int jb, int je, int kb, int ke, int nz, int side,
+			     double* u, const double* mu, const double* la, const double* met,
+			     const double* forcing, const double* strx, const double* stry, void* stream )
+{
+   if( need_init() ) return 1;
+   return launch_freesurfcurvisg( make_block( corder, ib, ie, jb, je, kb, ke ), nz, side, u, mu, la, met, forcing,
+				  strx, stry, as_stream( stream ) );
+}
+int sw4b200_enforce_cart_topo( int corder, double* ucart, int ib, int ie, int jb, int je, int kb, int ke,
+			       double* ucurv, int ckb, int cke, void* stream )
+{
+   if( need_init() ) return 1;
+   return launch_enforce_cart_topo( corder, ucart, make_block( corder, ib, ie, jb, je, kb, ke ), ucurv,
+				    make_block( corder, ib, ie, jb, je, ckb, cke ), as_stream( stream ) );
+}
+
+int sw4b200_add_point_forces( int corder, size_t npts, double* up, const double* rho, int n, const long long* pidx_,
+			      const double* f, double factor, void* stream )
+{
+   if( need_init() ) return 1;
+   return launch_add_point_forces( corder, (long long)npts, up, rho, n, pidx_, f, factor, as_stream( stream ) );
+}
+int sw4b200_gather_points( int corder, size_t npts, const double* u, int n, const long long* pidx_, double* out,
+			   void* stream )
+{
+   if( need_init() ) return 1;
+   return launch_gather_points( corder, (long long)npts, u, n, pidx_, out, as_stream( stream ) );
+}
+
+// ---- host-buffer entry point: staging buffers are cached between calls of the same size
+int sw4b200_rhs4sg_host( int corder, int ifirst, int ilast, int jfirst, int jlast, int kfirst, int klast, int nk,
+			 const int* onesided, double* h_lu, const double* h_u, const double* h_mu,
+			 const double* h_la, double h, const double* h_strx, const double* h_stry,
+			 const double* h_strz )
+{
+   if( need_init() ) return 1;
+   static double* dbuf = 0;
+   static size_t dcap = 0;
+   const Block b = make_block( corder, ifirst, ilast, jfirst, jlast, kfirst, klast );
+   const size_t n = (size_t)b.npts;
+   const size_t need = ( 8 * n + b.ni + b.nj + b.nk + 64 ) * sizeof( double );
+   if( need > dcap )
+   {
+      if( dbuf ) cudaFree( dbuf );
+      dbuf = 0; dcap = 0;
+      CUDA_OK( cudaMalloc( (void**)&dbuf, need ) );
+      dcap = need;
+   }
+   double* d_lu = dbuf; double* d_u = d_lu + 3 * n; double* d_mu = d_u + 3 * n; double* d_la = d_mu + n;
+   double* d_sx = d_la + n; double* d_sy = d_sx + b.ni; double* d_sz = d_sy + b.nj;
+   cudaStream_t st = g_streams[0];
+   CUDA_OK( cudaMemcpyAsync( d_u, h_u, 3 * n * 8, cudaMemcpyHostToDevice, st ) );
+   CUDA_OK( cudaMemcpyAsync( d_mu, h_mu, n * 8, cudaMemcpyHostToDevice, st ) );
+   CUDA_OK( cudaMemcpyAsync( d_la, h_la, n * 8, cudaMemcpyHostToDevice, st ) );
+   CUDA_OK( cudaMemcpyAsync( d_sx, h_strx, b.ni * 8, cudaMemcpyHostToDevice, st ) );
+   CUDA_OK( cudaMemcpyAsync( d_sy, h_stry, b.nj * 8, cudaMemcpyHostToDevice, st ) );
+   CUDA_OK( cudaMemcpyAsync( d_sz, h_strz, b.nk * 8, cudaMemcpyHostToDevice, st ) );
+   // the reference leaves lu untouched outside the interior: start from the caller's values
+   CUDA_OK( cudaMemcpyAsync( d_lu, h_lu, 3 * n * 8, cudaMemcpyHostToDevice, st ) );
+   if( sw4b200_rhs4sg( corder, ifirst, ilast, jfirst, jlast, kfirst, klast, nk, onesided, d_lu, d_u, d_mu, d_la, h,
+		       d_sx, d_sy, d_sz, st ) )
+      return 1;
+   CUDA_OK( cudaMemcpyAsync( h_lu, d_lu, 3 * n * 8, cudaMemcpyDeviceToHost, st ) );
+   CUDA_OK( cudaStreamSynchronize( st ) );
+   return 0;
+}
+
+// ------------------------------------------------------------------ grid-block solver object
+static double** grid_array( sw4b200_grid* g, const char* name, size_t* n )
+{
+   const std::string w( name );
+   const size_t np = (size_t)g->b.npts;
+   if( w == "U" ) { *n = 3 * np; return &g->U; }
+   if( w == "Um" ) { *n = 3 * np; return &g->Um; }
+   if( w == "Up" ) { *n = 3 * np; return &g->Up; }
+   if( w == "mu" ) { *n = np; return &g->mu; }
+   if( w == "lambda" ) { *n = np; return &g->la; }
+   if( w == "rho" ) { *n = np; return &g->rho; }
+   if( w == "jac" ) { *n = np; return &g->jac; }
+   if( w == "metric" ) { *n = 4 * np; return &g->met; }
+   const char* dn[3] = { "x", "y", "z" };
+   const size_t dl[3] = { (size_t)g->b.ni, (size_t)g->b.nj, (size_t)g->b.nk };
+   for( int d = 0; d < 3; d++ )
+   {
+      if( w == std::string( "str" ) + dn[d] ) { *n = dl[d]; return &g->str[d]; }
+      if( w == std::string( "dc" ) + dn[d] ) { *n = dl[d]; return &g->dc[d]; }
+      if( w == std::string( "co" ) + dn[d] ) { *n = dl[d]; return &g->co[d]; }
+   }
+   if( w.size() == 7 && w.substr( 0, 6 ) == "bforce" && w[6] >= '0' && w[6] <= '5' )
+   {
+      const int s = w[6] - '0';
+      *n = g->nbf[s];
+      return &g->bforce[s];
+   }
+   return 0;
+}
+
+sw4b200_grid* sw4b200_grid_create( const sw4b200_grid_desc* desc )
+{
+   if( need_init() ) return 0;
+   if( check_bounds( desc->ifirst, desc->ilast, desc->jfirst, desc->jlast, desc->kfirst, desc->klast ) ) return 0;
+   sw4b200_grid* g = new sw4b200_grid;
+   memset( g, 0, sizeof( *g ) );
+   g->d = *desc;
+   g->b = make_block( desc->corder, desc->ifirst, desc->ilast, desc->jfirst, desc->jlast, desc->kfirst, desc->klast );
+   g->st = g_streams[0];
+   const size_t np = (size_t)g->b.npts;
+   double** three[4] = { &g->U, &g->Um, &g->Up, &g->Up2 };
+   for( int a = 0; a < 4; a++ )
+   {
+      *three[a] = (double*)sw4b200_malloc( 3 * np * 8 );
+      if( !*three[a] ) return 0;
+      cudaMemsetAsync( *three[a], 0, 3 * np * 8, g->st );
+   }
+   double** one[3] = { &g->mu, &g->la, &g->rho };
+   for( int a = 0; a < 3; a++ )
+      if( !( *one[a] = (double*)sw4b200_malloc( np * 8 ) ) ) return 0;
+   if( desc->curvilinear )
+   {
+      if( !( g->jac = (double*)sw4b200_malloc( np * 8 ) ) ) return 0;
+      if( !( g->met = (double*)sw4b200_malloc( 4 * np * 8 ) ) ) return 0;
+   }
+   const size_t dl[3] = { (size_t)g->b.ni, (size_t)g->b.nj, (size_t)g->b.nk };
+   for( int d = 0; d < 3; d++ )
+   {
+      g->str[d] = (double*)sw4b200_malloc( dl[d] * 8 );
+      g->dc[d] = (double*)sw4b200_malloc( dl[d] * 8 );
+      g->co[d] = (double*)sw4b200_malloc( dl[d] * 8 );
+      if( !g->str[d] || !g->dc[d] || !g->co[d] ) return 0;
+      std::vector<double> ones( dl[d], 1.0 ), zeros( dl[d], 0.0 );
+      cudaMemcpy( g->str[d], ones.data(), dl[d] * 8, cudaMemcpyHostToDevice );
+      cudaMemcpy( g->co[d], ones.data(), dl[d] * 8, cudaMemcpyHostToDevice );
+      cudaMemcpy( g->dc[d], zeros.data(), dl[d] * 8, cudaMemcpyHostToDevice );
+   }
+   for( int s = 0; s < 6; s++ )
+   {
+      const int* w = desc->wind + 6 * s;
+      const int t = desc->bctype[s];
+      g->nbf[s] = 0;
+      if( t == 0 || t == 1 || t == 2 )
+      {
+	 const long long n = (long long)( w[1] - w[0] + 1 ) * ( w[3] - w[2] + 1 ) * ( w[5] - w[4] + 1 );
+	 if( n > 0 )
+	 {
+	    g->nbf[s] = 3 * (size_t)n;
+	    if( !( g->bforce[s] = (double*)sw4b200_malloc( g->nbf[s] * 8 ) ) ) return 0;
+	    cudaMemsetAsync( g->bforce[s], 0, g->nbf[s] * 8, g->st );
+	 }
+      }
+   }
+   for( int s = 0; s < 2; s++ )
+      if( !( g->halo_buf[s] = (double*)sw4b200_malloc( 6 * (size_t)g->b.nij * 8 ) ) ) return 0;
+   cudaStreamSynchronize( g->st );
+   return g;
+}
+
+int sw4b200_grid_destroy( sw4b200_grid* g )
+{
+   if( !g ) return 0;
+   cudaStreamSynchronize( g->st );
+   double* ptrs[] = { g->U, g->Um, g->Up, g->Up2, g->mu, g->la, g->rho, g->jac, g->met, g->d_f, g->d_rec,
+		      g->halo_buf[0], g->halo_buf[1] };
+   for( double* p : ptrs ) if( p ) cudaFree( p );
+   for( int d = 0; d < 3; d++ ) { cudaFree( g->str[d] ); cudaFree( g->dc[d] ); cudaFree( g->co[d] ); }
+   for( int s = 0; s < 6; s++ ) if( g->bforce[s] ) cudaFree( g->bforce[s] );
+   if( g->d_srcidx ) cudaFree( g->d_srcidx );
+   if( g->d_recidx ) cudaFree( g->d_recidx );
+   if( g->h_f ) cudaFreeHost( g->h_f );
+   if( g->h_rec ) cudaFreeHost( g->h_rec );
+   delete g;
+   return 0;
+}
+
+int sw4b200_grid_upload( sw4b200_grid* g, const char* name, const double* h_src )
+{
+   size_t n = 0;
+   double** p = grid_array( g, name, &n );
+   if( !p || !*p ) return set_error( "grid_upload: unknown or unallocated array '%s'", name );
+   CUDA_OK( cudaMemcpyAsync( *p, h_src, n * 8, cudaMemcpyHostToDevice, g->st ) );
+   CUDA_OK( cudaStreamSynchronize( g->st ) );
+   return 0;
+}
+int sw4b200_grid_download( sw4b200_grid* g, const char* name, double* h_dst )
+{
+   size_t n = 0;
+   double** p = grid_array( g, name, &n );
+   if( !p || !*p ) return set_error( "grid_download: unknown or unallocated array '%s'", name );
+   CUDA_OK( cudaMemcpyAsync( h_dst, *p, n * 8, cudaMemcpyDeviceToHost, g->st ) );
+   CUDA_OK( cudaStreamSynchronize( g->st ) );
+   return 0;
+}
+void* sw4b200_grid_device_ptr( sw4b200_grid* g, const char* name )
+{
+   size_t n = 0;
+   double** p = grid_array( g, name, &n );
+   return p ? (void*)*p : 0;
+}
+size_t sw4b200_grid_array_size( sw4b200_grid* g, const char* name )
+{
+   size_t n = 0;
+   double** p = grid_array( g, name, &n );
+   return p ? n : 0;
+}
+
+static int set_points( sw4b200_grid* g, int n, const int* ijk, long long** d_idx )
+{
+   if( *d_idx ) { cudaFree( *d_idx ); *d_idx = 0; }
+   if( n <= 0 ) return 0;
+   std::vector<long long> idx( n );
+   for( int s = 0; s < n; s++ )
+   {
+      const int i = ijk[3 * s], j = ijk[3 * s + 1], k = ijk[3 * s + 2];
+      if( i < g->b.ifirst || i > g->b.ilast || j < g->b.jfirst || j > g->b.jlast || k < g->b.kfirst || k > g->b.klast )
+	 return set_error( "point (%d,%d,%d) is outside the block", i, j, k );
+      idx[s] = pidx( g->b, i, j, k );
+   }
+   CUDA_OK( cudaMalloc( (void**)d_idx, n * sizeof( long long ) ) );
+   CUDA_OK( cudaMemcpy( *d_idx, idx.data(), n * sizeof( long long ), cudaMemcpyHostToDevice ) );
+   return 0;
+}
+
+int sw4b200_grid_set_source_points( sw4b200_grid* g, int n, const int* ijk )
+{
+   if( set_points( g, n, ijk, &g->d_srcidx ) ) return 1;
+   if( g->d_f ) { cudaFree( g->d_f ); g->d_f = 0; }
+   if( g->h_f ) { cudaFreeHost( g->h_f ); g->h_f = 0; }
+   g->nsrc = n > 0 ? n : 0;
+   if( n > 0 )
+   {
+      CUDA_OK( cudaMalloc( (void**)&g->d_f, 2 * 3 * n * sizeof( double ) ) );
+      CUDA_OK( cudaMallocHost( (void**)&g->h_f, 2 * 3 * n * sizeof( double ) ) );
+   }
+   return 0;
+}
+int sw4b200_grid_set_receiver_points( sw4b200_grid* g, int n, const int* ijk )
+{
+   if( set_points( g, n, ijk, &g->d_recidx ) ) return 1;
+   if( g->d_rec ) { cudaFree( g->d_rec ); g->d_rec = 0; }
+   if( g->h_rec ) { cudaFreeHost( g->h_rec ); g->h_rec = 0; }
+   g->nrec = n > 0 ? n : 0;
+   if( n > 0 )
+   {
+      CUDA_OK( cudaMalloc( (void**)&g->d_rec, 3 * n * sizeof( double ) ) );
+      CUDA_OK( cudaMallocHost( (void**)&g->h_rec, 3 * n * sizeof( double ) ) );
+   }
+   return 0;
+}
+
+static void fill_args( sw4b200_grid* g, RhsArgs& a )
+{
+   memset( &a, 0, sizeof( a ) );
+   a.b = g->b;
+   a.nk = g->d.nz;
+   a.onesided4 = g->d.onesided[4] == 1;
+   a.onesided5 = g->d.onesided[5] == 1;
+   a.mu = g->mu; a.la = g->la; a.rho = g->rho;
+   a.strx = g->str[0]; a.stry = g->str[1]; a.strz = g->str[2];
+   a.dcx = g->dc[0]; a.dcy = g->dc[1]; a.dcz = g->dc[2];
+   a.cox = g->co[0]; a.coy = g->co[1]; a.coz = g->co[2];
+   a.h = g->d.h; a.dt = g->d.dt;
+   a.beta = g->d.beta;
+   a.sg_order = g->d.beta == 0 ? 0 : g->d.sg_order;
+}
+
+static int inject( sw4b200_grid* g, const double* h_f, int slot, double factor )
+{
+   if( g->nsrc == 0 || h_f == 0 ) return 0;
+   double* hp = g->h_f + slot * 3 * g->nsrc;
+   double* dp = g->d_f + slot * 3 * g->nsrc;
+   memcpy( hp, h_f, 3 * g->nsrc * sizeof( double ) );
+   CUDA_OK( cudaMemcpyAsync( dp, hp, 3 * g->nsrc * sizeof( double ), cudaMemcpyHostToDevice, g->st ) );
+   return launch_add_point_forces( g->d.corder, g->b.npts, g->Up, g->rho, g->nsrc, g->d_srcidx, dp, factor, g->st );
+}
+
+static int curv_predictor( sw4b200_grid* g, const double* h_f );
+static int curv_corrector( sw4b200_grid* g, const double* h_ftt );
+
+int sw4b200_grid_predictor( sw4b200_grid* g, const double* h_f )
+{
+   RhsArgs a;
+   fill_args( g, a );
+   if( g->d.curvilinear ) return curv_predictor( g, h_f );
+   a.out = g->Up; a.u = g->U; a.um = g->Um; a.fo = 0;
+   if( run_rhs( MODE_PRED, a, g->d.corder, g->st ) ) return 1;
+   return inject( g, h_f, 0, g->d.dt * g->d.dt );
+}
+
+int sw4b200_grid_enforce_bc( sw4b200_grid* g )
+{
+   Int36 w; Int6 bc; Ptr6 bf;
+   for( int s = 0; s < 36; s++ ) w.v[s] = g->d.wind[s];
+   for( int s = 0; s < 6; s++ ) { bc.v[s] = g->d.bctype[s]; bf.p[s] = g->bforce[s]; }
+   if( g->d.halo_lo ) bc.v[4] = 7;
+   if( g->d.halo_hi ) bc.v[5] = 7;
+   if( launch_bcfortsg( g->b, w, g->d.nx, g->d.ny, g->d.nz, g->Up, g->d.h, bc, g->mu, g->la, bf, g->str[0], g->str[1], g->st ) )
+      return 1;
+   if( g->d.curvilinear && g->d.bctype[4] == 0 && !g->d.halo_lo )
+      return launch_freesurfcurvisg( g->b, g->d.nz, 5, g->Up, g->mu, g->la, g->met, g->bforce[4], g->str[0], g->str[1], g->st );
+   return 0;
+}
+
+int sw4b200_grid_corrector( sw4b200_grid* g, const double* h_ftt )
+{
+   RhsArgs a;
+   fill_args( g, a );
+   if( g->d.curvilinear ) return curv_corrector( g, h_ftt );
+   a.out = g->Up2; a.up = g->Up; a.u = g->U; a.um = g->Um; a.fo = 0;
+   if( run_rhs( MODE_CORR, a, g->d.corder, g->st ) ) return 1;
+   double* t = g->Up; g->Up = g->Up2; g->Up2 = t;
+   const double dt2 = g->d.dt * g->d.dt;
+   return inject( g, h_ftt, 1, dt2 * dt2 / 12 );
+}
+
+// curvilinear grid block: unfused sequence rhs4sgcurv -> predictor / dpdmt -> rhs4sgcurv -> corrector
+// -> addsgd4c, with Up2 as the L(u) scratch array (zero on the shell, like the reference's Lu)
+static int curv_predictor( sw4b200_grid* g, const double* h_f )
+{
+   (void)g; (void)h_f;
+   return set_error( "curvilinear grid blocks are not implemented yet" );
+}
+static int curv_corrector( sw4b200_grid* g, const double* h_ftt )
+{
+   (void)g; (void)h_ftt;
+   return set_error( "curvilinear grid blocks are not implemented yet" );
+}
+
+int sw4b200_grid_cycle( sw4b200_grid* g )
+{
+   double* t = g->Um;
+   g->Um = g->U; g->U = g->Up; g->Up = t;
+   return 0;
+}
+
+int sw4b200_grid_record( sw4b200_grid* g, double* h_out )
+{
+   if( g->nrec == 0 ) return 0;
+   if( launch_gather_points( g->d.corder, g->b.npts, g->Up, g->nrec, g->d_recidx, g->d_rec, g->st ) ) return 1;
+   CUDA_OK( cudaMemcpyAsync( g->h_rec, g->d_rec, 3 * g->nrec * sizeof( double ), cudaMemcpyDeviceToHost, g->st ) );
+   CUDA_OK( cudaStreamSynchronize( g->st ) );
+   memcpy( h_out, g->h_rec, 3 * g->nrec * sizeof( double ) );
+   return 0;
+}
+
+int sw4b200_grid_step( sw4b200_grid* g, const double* h_f, const double* h_ftt, double* h_rec )
+{
+   if( sw4b200_grid_predictor( g, h_f ) ) return 1;
+   if( sw4b200_grid_enforce_bc( g ) ) return 1;
+   if( sw4b200_grid_corrector( g, h_ftt ) ) return 1;
+   if( sw4b200_grid_enforce_bc( g ) ) return 1;
+   if( h_rec && sw4b200_grid_record( g, h_rec ) ) return 1;
+   return sw4b200_grid_cycle( g );
+}
+
+int sw4b200_grid_pack_halo( sw4b200_grid* g, int side, double* d_dst, void* stream )
+{
+   // interior planes next to the face: local plane offsets 2,3 (low) or nk-4,nk-3 (high)
+   const int kplane = side == 0 ? 2 : g->b.nk - 4;
+   return launch_halo_copy( g->b, g->Up, kplane, d_dst, 1, stream ? (cudaStream_t)stream : g->st );
+}
+int sw4b200_grid_unpack_halo( sw4b200_grid* g, int side, const double* d_src, void* stream )
+{
+   const int kplane = side == 0 ? 0 : g->b.nk - 2;
+   return launch_halo_copy( g->b, g->Up, kplane, (double*)d_src, 0, stream ? (cudaStream_t)stream : g->st );
+}
+int sw4b200_grid_sync( sw4b200_grid* g )
+{
+   CUDA_OK( cudaStreamSynchronize( g->st ) );
+   return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,696 @@
+// Cartesian-grid operators, general (layout-agnostic) CUDA kernels: one thread per grid point,
+// neighbours through L1/L2.  These are the correctness baseline for every layout/option
+// (AoS and SoA, both closures, 6th-order damping, dense forcing) and the path used for the
+// thin SBP-closure rows and the ghost shell.  The throughput path for the SoA interior is
+// rhs4sg_fast.cu.
+//
+// Reference semantics: rhs4sg.C:38-849 / rhs4sg_rev.C:44-864 (L(u)), ew-cfromfort.C:40-141
+// (corrector, predictor, dpdmt), :748-1160 (supergrid damping), :205-745 (bcfortsg).
+#include "common.cuh"
+
+namespace sw4b200 {
+
+#define ACOF( k, q, m ) c_acof[( (k)-1 ) + 6 * ( (q)-1 ) + 48 * ( (m)-1 )]
+#define BOPE( k, q ) c_bope[( (k)-1 ) + 6 * ( (q)-1 )]
+
+namespace {
+
+template <int MODE>
+struct Acc
+{
+   const double *u, *um, *up;
+   long long sc, sp;
+   double dt2i;
+   __device__ __forceinline__ double operator()( int c, long long p ) const
+   {
+      const long long q = c * sc + sp * p;
+      if( MODE == MODE_CORR )
+	 return dt2i * ( up[q] - 2 * u[q] + um[q] );
+      return u[q];
+   }
+};
+
+__device__ __forceinline__ void weights4( const double a[5], double w[4] )
+{
+   w[0] = a[1] - 0.75 * ( a[2] + a[0] );
+   w[1] = a[0] + a[3] + 3 * ( a[2] + a[1] );
+   w[2] = a[1] + a[4] + 3 * ( a[3] + a[2] );
+   w[3] = a[3] - 0.75 * ( a[2] + a[4] );
+}
+__device__ __forceinline__ double gsum( const double w[4], const double f[5] )
+{
+   return w[0] * ( f[0] - f[2] ) + w[1] * ( f[1] - f[2] ) + w[2] * ( f[3] - f[2] ) + w[3] * ( f[4] - f[2] );
+}
+__device__ __forceinline__ double d0( double fm2, double fm1, double fp1, double fp2 )
+{
+   return ( fm2 - fp2 + 8 * ( fp1 - fm1 ) ) * ( 1.0 / 12 );
+}
+
+// second-derivative terms in direction with stride st; s[5] = stretch at the 5 points; comp d is "normal"
+template <class A>
+__device__ __forceinline__ void second_derivative( const A& U, const double* __restrict__ mu,
+						   const double* __restrict__ la, long long p, long long st,
+						   const double s[5], int d, double r[3] )
+{
+   double am[5], bm[5], wm[4], wb[4], f[5];
+#pragma unroll
+   for( int m = 0; m < 5; m++ )
+   {
+      const double mm = mu[p + ( m - 2 ) * st];
+      am[m] = mm * s[m];
+      bm[m] = ( 2 * mm + la[p + ( m - 2 ) * st] ) * s[m];
+   }
+   weights4( am, wm );
+   weights4( bm, wb );
+#pragma unroll
+   for( int c = 0; c < 3; c++ )
+   {
+#pragma unroll
+      for( int m = 0; m < 5; m++ ) f[m] = U( c, p + ( m - 2 ) * st );
+      r[c] += ( 1.0 / 6 ) * s[2] * gsum( c == d ? wb : wm, f );
+   }
+}
+
+// s_a s_b [ D0_a( la D0_b u_b ) + D0_b( mu D0_a u_b ) ] added to r_a
+template <class A>
+__device__ __forceinline__ double mixed_pair( const A& U, const double* __restrict__ mu,
+					      const double* __restrict__ la, long long p, long long sa,
+					      long long sb, int b )
+{
+   double t1[5], t2[5];
+#pragma unroll
+   for( int m = 0; m < 5; m++ )
+   {
+      if( m == 2 ) continue;
+      long long q = p + ( m - 2 ) * sa;
+      t1[m] = la[q] * d0( U( b, q - 2 * sb ), U( b, q - sb ), U( b, q + sb ), U( b, q + 2 * sb ) );
+      q = p + ( m - 2 ) * sb;
+      t2[m] = mu[q] * d0( U( b, q - 2 * sa ), U( b, q - sa ), U( b, q + sa ), U( b, q + 2 * sa ) );
+   }
+   return d0( t1[0], t1[1], t1[3], t1[4] ) + d0( t2[0], t2[1], t2[3], t2[4] );
+}
+
+template <class A>
+__device__ void rhs_interior_point( const A& U, const double* __restrict__ mu, const double* __restrict__ la,
+				    long long p, long long dj, long long dk, const double sx[5],
+				    const double sy[5], const double sz[5], double r[3] )
+{
+   r[0] = r[1] = r[2] = 0;
+   second_derivative( U, mu, la, p, 1LL, sx, 0, r );
+   second_derivative( U, mu, la, p, dj, sy, 1, r );
+   second_derivative( U, mu, la, p, dk, sz, 2, r );
+   r[0] += sx[2] * sy[2] * mixed_pair( U, mu, la, p, 1LL, dj, 1 ) + sx[2] * sz[2] * mixed_pair( U, mu, la, p, 1LL, dk, 2 );
+   r[1] += sx[2] * sy[2] * mixed_pair( U, mu, la, p, dj, 1LL, 0 ) + sy[2] * sz[2] * mixed_pair( U, mu, la, p, dj, dk, 2 );
+   r[2] += sx[2] * sz[2] * mixed_pair( U, mu, la, p, dk, 1LL, 0 ) + sy[2] * sz[2] * mixed_pair( U, mu, la, p, dk, dj, 1 );
+}
+
+// SBP closure row kb (1..6) of side (0: low-k, planes q -> k=q; 1: high-k, planes q -> nk-q+1).
+// pcol = index of (i,j,k=kfirst) column base; plane(k) = pcol + dk*(k-kfirst).
+template <class A>
+__device__ void rhs_closure_point( const A& U, const double* __restrict__ mu, const double* __restrict__ la,
+				   long long pcol, int kfirst, int nk, int side, int kb, long long dj,
+				   long long dk, const double sx[5], const double sy[5], double r[3] )
+{
+   auto plane = [&]( int q ) -> long long {
+      const int k = side == 0 ? q : nk - q + 1;
+      return pcol + dk * ( k - kfirst );
+   };
+   const double sgn = side == 0 ? 1.0 : -1.0;
+   const long long p = plane( kb );
+   r[0] = r[1] = r[2] = 0;
+   second_derivative( U, mu, la, p, 1LL, sx, 0, r );
+   second_derivative( U, mu, la, p, dj, sy, 1, r );
+   // z second derivative, boundary-modified, no strz and no 1/6
+   double muq[8], laq[8];
+#pragma unroll
+   for( int m = 0; m < 8; m++ )
+   {
+      muq[m] = mu[plane( m + 1 )];
+      laq[m] = 2 * muq[m] + la[plane( m + 1 )];
+   }
+   for( int q = 1; q <= 8; q++ )
+   {
+      double mucof = 0, lap2mu = 0;
+#pragma unroll
+      for( int m = 1; m <= 8; m++ )
+      {
+	 const double a = ACOF( kb, q, m );
+	 mucof += a * muq[m - 1];
+	 lap2mu += a * laq[m - 1];
+      }
+      const long long pq = plane( q );
+      r[0] += mucof * U( 0, pq );
+      r[1] += mucof * U( 1, pq );
+      r[2] += lap2mu * U( 2, pq );
+   }
+   {
+      const long long pg = plane( 0 );
+      const double g = c_ghcof[kb - 1];
+      r[0] += g * muq[0] * U( 0, pg );
+      r[1] += g * muq[0] * U( 1, pg );
+      r[2] += g * laq[0] * U( 2, pg );
+   }
+   // xy cross terms, centred
+   r[0] += sx[2] * sy[2] * mixed_pair( U, mu, la, p, 1LL, dj, 1 );
+   r[1] += sx[2] * sy[2] * mixed_pair( U, mu, la, p, dj, 1LL, 0 );
+   // terms with one z-derivative: D0z -> sgn*sum_q bope(kb,q) f(plane q)
+#pragma unroll
+   for( int a = 0; a < 2; a++ )
+   {
+      const long long sa = a == 0 ? 1LL : dj;
+      const double fa = a == 0 ? sx[2] : sy[2];
+      double bw[5], bu[5];
+#pragma unroll
+      for( int m = 0; m < 5; m++ )
+      {
+	 bw[m] = bu[m] = 0;
+	 if( m == 2 ) continue;
+	 for( int q = 1; q <= 8; q++ )
+	 {
+	    const long long pq = plane( q ) + ( m - 2 ) * sa;
+	    const double bq = sgn * BOPE( kb, q );
+	    bw[m] += bq * U( 2, pq );
+	    bu[m] += bq * U( a, pq );
+	 }
+	 bw[m] *= la[p + ( m - 2 ) * sa];
+	 bu[m] *= mu[p + ( m - 2 ) * sa];
+      }
+      double zmw = 0, zlu = 0;
+      for( int q = 1; q <= 8; q++ )
+      {
+	 const long long pq = plane( q );
+	 const double bq = sgn * BOPE( kb, q );
+	 zmw += bq * ( muq[q - 1] * d0( U( 2, pq - 2 * sa ), U( 2, pq - sa ), U( 2, pq + sa ), U( 2, pq + 2 * sa ) ) );
+	 zlu += bq * ( la[pq] * d0( U( a, pq - 2 * sa ), U( a, pq - sa ), U( a, pq + sa ), U( a, pq + 2 * sa ) ) );
+      }
+      r[a] += fa * ( d0( bw[0], bw[1], bw[3], bw[4] ) + zmw );
+      r[2] += fa * ( d0( bu[0], bu[1], bu[3], bu[4] ) + zlu );
+   }
+}
+
+// supergrid damping of one point, all three components: returns sum_d pre_d * D_d(...)
+__device__ __forceinline__ double sgd_point( int order, const double* __restrict__ u, const double* __restrict__ um,
+					     const double* __restrict__ rho, long long q, long long p,
+					     long long sp, long long st, const double* dc, double pre )
+{
+   // q = index of component value at the point in u/um; point stride in u is sp*st
+   const long long su = sp * st;
+   if( order == 4 )
+   {
+      double d[5];
+#pragma unroll
+      for( int m = 0; m < 5; m++ ) d[m] = u[q + ( m - 2 ) * su] - um[q + ( m - 2 ) * su];
+      const double e0 = rho[p - st] * dc[-1] * ( d[2] - 2 * d[1] + d[0] );
+      const double e1 = rho[p] * dc[0] * ( d[3] - 2 * d[2] + d[1] );
+      const double e2 = rho[p + st] * dc[1] * ( d[4] - 2 * d[3] + d[2] );
+      return pre * ( e2 - 2 * e1 + e0 );
+   }
+   else
+   {
+      double d[7];
+#pragma unroll
+      for( int m = 0; m < 7; m++ ) d[m] = u[q + ( m - 3 ) * su] - um[q + ( m - 3 ) * su];
+      double acc = 0;
+      const double cw[4] = { -1, 3, -3, 1 };
+#pragma unroll
+      for( int m = -2; m <= 1; m++ )
+      {
+	 const double A = rho[p + ( m + 1 ) * st] * dc[m + 1] + rho[p + m * st] * dc[m];
+	 const double T = d[m + 5] - 3 * d[m + 4] + 3 * d[m + 3] - d[m + 2];
+	 acc += cw[m + 2] * A * T;
+      }
+      return pre * ( -0.5 * acc );
+   }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__( 256 ) k_rhs_v1( RhsArgs a, int k_lo, int k_hi )
+{
+   const Block& b = a.b;
+   const int i = b.ifirst + 2 + blockIdx.x * blockDim.x + threadIdx.x;
+   const int j = b.jfirst + 2 + blockIdx.y * blockDim.y + threadIdx.y;
+   const int k = k_lo + blockIdx.z * blockDim.z + threadIdx.z;
+   if( i > b.ilast - 2 || j > b.jlast - 2 || k > k_hi ) return;
+   Acc<MODE> U = { a.u, a.um, a.up, b.sc, b.sp, 1.0 / ( a.dt * a.dt ) };
+   double sx[5], sy[5], sz[5];
+#pragma unroll
+   for( int m = 0; m < 5; m++ )
+   {
+      sx[m] = a.strx[i - b.ifirst + m - 2];
+      sy[m] = a.stry[j - b.jfirst + m - 2];
+   }
+   const long long p = pidx( b, i, j, k );
+   double r[3];
+   const bool low = a.onesided4 && k <= 6;
+   const bool high = a.onesided5 && k >= a.nk - 5;
+   if( low || high )
+   {
+      const long long pcol = pidx( b, i, j, b.kfirst );
+      rhs_closure_point( U, a.mu, a.la, pcol, b.kfirst, a.nk, low ? 0 : 1, low ? k : a.nk - k + 1,
+			 (long long)b.ni, b.nij, sx, sy, r );
+   }
+   else
+   {
+#pragma unroll
+      for( int m = 0; m < 5; m++ ) sz[m] = a.strz[k - b.kfirst + m - 2];
+      rhs_interior_point( U, a.mu, a.la, p, (long long)b.ni, b.nij, sx, sy, sz, r );
+   }
+   const double cof = 1.0 / ( a.h * a.h );
+   if( MODE == MODE_LU )
+   {
+#pragma unroll
+      for( int c = 0; c < 3; c++ ) a.out[c * b.sc + b.sp * p] = cof * r[c];
+   }
+   else if( MODE == MODE_PRED )
+   {
+      const double f = ( a.dt * a.dt ) / a.rho[p];
+#pragma unroll
+      for( int c = 0; c < 3; c++ )
+      {
+	 const long long q = c * b.sc + b.sp * p;
+	 const double fo = a.fo ? a.fo[q] : 0.0;
+	 a.out[q] = 2 * a.u[q] - a.um[q] + f * ( cof * r[c] + fo );
+      }
+   }
+   else
+   {
+      const double dt2 = a.dt * a.dt;
+      const double f = ( dt2 * dt2 / 12 ) / a.rho[p];
+      double sg[3] = { 0, 0, 0 };
+      const int w = a.sg_order == 6 ? 3 : 2;
+      if( a.sg_order != 0 && a.beta != 0 && i >= b.ifirst + w && i <= b.ilast - w && j >= b.jfirst + w &&
+	  j <= b.jlast - w && k >= b.kfirst + w && k <= b.klast - w )
+      {
+	 const int ii = i - b.ifirst, jj = j - b.jfirst, kk = k - b.kfirst;
+	 const double prex = a.strx[ii] * a.coy[jj] * a.coz[kk];
+	 const double prey = a.stry[jj] * a.cox[ii] * a.coz[kk];
+	 const double prez = a.strz[kk] * a.cox[ii] * a.coy[jj];
+	 const double birho = a.beta / a.rho[p];
+#pragma unroll
+	 for( int c = 0; c < 3; c++ )
+	 {
+	    const long long q = c * b.sc + b.sp * p;
+	    sg[c] = birho * ( sgd_point( a.sg_order, a.u, a.um, a.rho, q, p, b.sp, 1LL, a.dcx + ii, prex ) +
+			      sgd_point( a.sg_order, a.u, a.um, a.rho, q, p, b.sp, (long long)b.ni, a.dcy + jj, prey ) +
+			      sgd_point( a.sg_order, a.u, a.um, a.rho, q, p, b.sp, b.nij, a.dcz + kk, prez ) );
+	 }
+      }
+#pragma unroll
+      for( int c = 0; c < 3; c++ )
+      {
+	 const long long q = c * b.sc + b.sp * p;
+	 const double fo = a.fo ? a.fo[q] : 0.0;
+	 a.out[q] = ( a.up[q] + f * ( cof * r[c] + fo ) ) - sg[c];
+      }
+   }
+}
+
+// the 2-point shell where L(u) is never written (stays 0 in the reference): pred/corr with lu=0.
+// Enumerates the shell as 6 slabs: k-low, k-high (full planes), j-low, j-high, i-low, i-high.
+template <int MODE>
+__global__ void k_shell_update( RhsArgs a )
+{
+   const Block& b = a.b;
+   const long long nkplane = 2 * b.nij;				   // per k side
+   const long long njslab = 2LL * b.ni * ( b.nk - 4 );		   // per j side
+   const long long nislab = 2LL * ( b.nj - 4 ) * ( b.nk - 4 );	   // per i side
+   const long long total = 2 * ( nkplane + njslab + nislab );
+   for( long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+	t += (long long)gridDim.x * blockDim.x )
+   {
+      long long s = t;
+      int i, j, k;
+      if( s < 2 * nkplane )
+      {
+	 const int side = s >= nkplane;
+	 s -= side * nkplane;
+	 k = (int)( s / b.nij );
+	 const long long rr = s % b.nij;
+	 j = (int)( rr / b.ni );
+	 i = (int)( rr % b.ni );
+	 if( side ) k += b.nk - 2;
+      }
+      else if( ( s -= 2 * nkplane ) < 2 * njslab )
+      {
+	 const int side = s >= njslab;
+	 s -= side * njslab;
+	 const long long per_k = 2LL * b.ni;
+	 k = 2 + (int)( s / per_k );
+	 const long long rr = s % per_k;
+	 j = (int)( rr / b.ni );
+	 i = (int)( rr % b.ni );
+	 if( side ) j += b.nj - 2;
+      }
+      else
+      {
+	 s -= 2 * njslab;
+	 const int side = s >= nislab;
+	 s -= side * nislab;
+	 const long long per_k = 2LL * ( b.nj - 4 );
+	 k = 2 + (int)( s / per_k );
+	 const long long rr = s % per_k;
+	 j = 2 + (int)( rr / 2 );
+	 i = (int)( rr % 2 );
+	 if( side ) i += b.ni - 2;
+      }
+      const long long p = (long long)i + (long long)b.ni * j + b.nij * k;
+      if( MODE == MODE_PRED )
+      {
+	 const double f = ( a.dt * a.dt ) / a.rho[p];
+#pragma unroll
+	 for( int c = 0; c < 3; c++ )
+	 {
+	    const long long q = c * b.sc + b.sp * p;
+	    const double fo = a.fo ? a.fo[q] : 0.0;
+	    a.out[q] = 2 * a.u[q] - a.um[q] + f * ( 0.0 + fo );
+	 }
+      }
+      else
+      {
+	 const double dt2 = a.dt * a.dt;
+	 const double f = ( dt2 * dt2 / 12 ) / a.rho[p];
+#pragma unroll
+	 for( int c = 0; c < 3; c++ )
+	 {
+	    const long long q = c * b.sc + b.sp * p;
+	    const double fo = a.fo ? a.fo[q] : 0.0;
+	    a.out[q] = a.up[q] + f * ( 0.0 + fo );
+	 }
+      }
+   }
+}
+
+__global__ void k_predfort( Block b, double* __restrict__ up, const double* __restrict__ u,
+			    const double* __restrict__ um, const double* __restrict__ lu,
+			    const double* __restrict__ fo, const double* __restrict__ rho, double dt2 )
+{
+   for( long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < b.npts;
+	p += (long long)gridDim.x * blockDim.x )
+   {
+      const double f = dt2 / rho[p];
+#pragma unroll
+      for( int c = 0; c < 3; c++ )
+      {
+	 const long long q = c * b.sc + b.sp * p;
+	 up[q] = 2 * u[q] - um[q] + f * ( lu[q] + fo[q] );
+      }
+   }
+}
+
+__global__ void k_corrfort( Block b, double* __restrict__ up, const double* __restrict__ lu,
+			    const double* __restrict__ fo, const double* __restrict__ rho, double dt4i12 )
+{
+   for( long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < b.npts;
+	p += (long long)gridDim.x * blockDim.x )
+   {
+      const double f = dt4i12 / rho[p];
+#pragma unroll
+      for( int c = 0; c < 3; c++ )
+      {
+	 const long long q = c * b.sc + b.sp * p;
+	 up[q] += f * ( lu[q] + fo[q] );
+      }
+   }
+}
+
+__global__ void k_dpdmt( long long n, const double* __restrict__ up, const double* __restrict__ u,
+			 const double* __restrict__ um, double* __restrict__ u2, double dt2i )
+{
+   for( long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n;
+	p += (long long)gridDim.x * blockDim.x )
+      u2[p] = dt2i * ( up[p] - 2 * u[p] + um[p] );
+}
+
+__global__ void k_addsgd( int order, Block b, double* __restrict__ up, const double* __restrict__ u,
+			  const double* __restrict__ um, const double* __restrict__ rho,
+			  const double* __restrict__ dcx, const double* __restrict__ dcy,
+			  const double* __restrict__ dcz, const double* __restrict__ strx,
+			  const double* __restrict__ stry, const double* __restrict__ strz,
+			  const double* __restrict__ cox, const double* __restrict__ coy,
+			  const double* __restrict__ coz, double beta )
+{
+   const int w = order == 6 ? 3 : 2;
+   const int ii = w + blockIdx.x * blockDim.x + threadIdx.x;
+   const int jj = w + blockIdx.y * blockDim.y + threadIdx.y;
+   const int kk = w + blockIdx.z * blockDim.z + threadIdx.z;
+   if( ii > b.ni - 1 - w || jj > b.nj - 1 - w || kk > b.nk - 1 - w ) return;
+   const long long p = (long long)ii + (long long)b.ni * jj + b.nij * kk;
+   const double prex = strx[ii] * coy[jj] * coz[kk];
+   const double prey = stry[jj] * cox[ii] * coz[kk];
+   const double prez = strz[kk] * cox[ii] * coy[jj];
+   const double birho = beta / rho[p];
+#pragma unroll
+   for( int c = 0; c < 3; c++ )
+   {
+      const long long q = c * b.sc + b.sp * p;
+      const double s = sgd_point( order, u, um, rho, q, p, b.sp, 1LL, dcx + ii, prex ) +
+		       sgd_point( order, u, um, rho, q, p, b.sp, (long long)b.ni, dcy + jj, prey ) +
+		       sgd_point( order, u, um, rho, q, p, b.sp, b.nij, dcz + kk, prez );
+      up[q] -= birho * s;
+   }
+}
+
+// Dirichlet / supergrid ghost fill and periodic copy for one side window
+__global__ void k_bc_window( Block b, int s, int i0, int i1, int j0, int j1, int k0, int k1, int type,
+			     long long off, double* __restrict__ u, const double* __restrict__ bf )
+{
+   const long long wi = i1 - i0 + 1, wj = j1 - j0 + 1, wk = k1 - k0 + 1;
+   const long long total = wi * wj * wk;
+   for( long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+	t += (long long)gridDim.x * blockDim.x )
+   {
+      const int i = i0 + (int)( t % wi );
+      const int j = j0 + (int)( ( t / wi ) % wj );
+      const int k = k0 + (int)( t / ( wi * wj ) );
+      const long long p = pidx( b, i, j, k );
+#pragma unroll
+      for( int c = 0; c < 3; c++ )
+      {
+	 const long long q = c * b.sc + b.sp * p;
+	 if( type == 3 )
+	    u[q] = u[q + b.sp * off];
+	 else
+	    u[q] = bf[3 * t + c];
+      }
+   }
+}
+
+// stress-free ghost plane of side 4 (k=1, kl=1) or 5 (k=nz, kl=-1)
+__global__ void k_bc_freesurface( Block b, int k, int kl, double h, double* __restrict__ u,
+				  const double* __restrict__ mu, const double* __restrict__ la,
+				  const double* __restrict__ bf, const double* __restrict__ strx,
+				  const double* __restrict__ stry )
+{
+   const int ii = 2 + blockIdx.x * blockDim.x + threadIdx.x;
+   const int jj = 2 + blockIdx.y * blockDim.y + threadIdx.y;
+   if( ii > b.ni - 3 || jj > b.nj - 3 ) return;
+   const double d4a = 2.0 / 3.0, d4b = -1.0 / 12.0;
+   const long long qq = (long long)ii + (long long)b.ni * jj;
+   const long long p = qq + b.nij * ( k - b.kfirst );
+   const long long sp = b.sp, sc = b.sc, dj = b.ni;
+   auto U = [&]( int c, long long pp ) { return u[c * sc + sp * pp]; };
+   const double sx = strx[ii], sy = stry[jj];
+   const double wx = sx * ( d4a * ( U( 2, p + 1 ) - U( 2, p - 1 ) ) + d4b * ( U( 2, p + 2 ) - U( 2, p - 2 ) ) );
+   const double ux = sx * ( d4a * ( U( 0, p + 1 ) - U( 0, p - 1 ) ) + d4b * ( U( 0, p + 2 ) - U( 0, p - 2 ) ) );
+   const double wy = sy * ( d4a * ( U( 2, p + dj ) - U( 2, p - dj ) ) + d4b * ( U( 2, p + 2 * dj ) - U( 2, p - 2 * dj ) ) );
+   const double vy = sy * ( d4a * ( U( 1, p + dj ) - U( 1, p - dj ) ) + d4b * ( U( 1, p + 2 * dj ) - U( 1, p - 2 * dj ) ) );
+   double uz = 0, vz = 0, wz = 0;
+#pragma unroll
+   for( int q = 1; q <= 4; q++ )
+   {
+      const long long pq = p + b.nij * ( kl * ( q - 1 ) );
+      uz += c_sbop[q] * U( 0, pq );
+      vz += c_sbop[q] * U( 1, pq );
+      wz += c_sbop[q] * U( 2, pq );
+   }
+   const long long pg = p - b.nij * kl;
+   const double m = mu[p], l = la[p];
+   const double b0 = bf ? bf[3 * qq] : 0.0, b1 = bf ? bf[3 * qq + 1] : 0.0, b2 = bf ? bf[3 * qq + 2] : 0.0;
+   u[0 * sc + sp * pg] = ( -uz - kl * wx + kl * h * b0 / m ) / c_sbop[0];
+   u[1 * sc + sp * pg] = ( -vz - kl * wy + kl * h * b1 / m ) / c_sbop[0];
+   u[2 * sc + sp * pg] = ( -wz + ( -kl * l * ( ux + vy ) + kl * h * b2 ) / ( 2 * m + l ) ) / c_sbop[0];
+}
+
+__global__ void k_add_point_forces( long long sc, long long sp, double* __restrict__ up,
+				    const double* __restrict__ rho, int n, const long long* __restrict__ pidx_,
+				    const double* __restrict__ f, double factor )
+{
+   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+   if( t >= n ) return;
+   const long long p = pidx_[t];
+   const double s = factor / rho[p];
+#pragma unroll
+   for( int c = 0; c < 3; c++ ) up[c * sc + sp * p] += s * f[3 * t + c];
+}
+
+__global__ void k_gather_points( long long sc, long long sp, const double* __restrict__ u, int n,
+				 const long long* __restrict__ pidx_, double* __restrict__ out )
+{
+   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+   if( t >= n ) return;
+   const long long p = pidx_[t];
+#pragma unroll
+   for( int c = 0; c < 3; c++ ) out[3 * t + c] = u[c * sc + sp * p];
+}
+
+// copy two k-planes (kplane, kplane+1 as local plane offsets) of a 3-component field to/from a
+// buffer laid out [c][2][nj][ni]
+__global__ void k_halo_copy( Block b, double* __restrict__ field, int kplane, double* __restrict__ buf, int pack )
+{
+   const long long n2 = 2 * b.nij;
+   for( long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < 3 * n2;
+	t += (long long)gridDim.x * blockDim.x )
+   {
+      const int c = (int)( t / n2 );
+      const long long r = t % n2;
+      const long long p = b.nij * kplane + r;
+      const long long q = c * b.sc + b.sp * p;
+      if( pack ) buf[t] = field[q];
+      else field[q] = buf[t];
+   }
+}
+
+inline int nblocks( long long n, int bs, int cap = 148 * 16 )
+{
+   long long g = ( n + bs - 1 ) / bs;
+   if( g > cap ) g = cap;
+   if( g < 1 ) g = 1;
+   return (int)g;
+}
+
+} // namespace
+
+int launch_rhs_v1( RhsMode mode, const RhsArgs& a, cudaStream_t st )
+{
+   const Block& b = a.b;
+   const int k_lo = b.kfirst + 2, k_hi = b.klast - 2;
+   if( k_hi < k_lo || b.ni < 5 || b.nj < 5 ) return 0;
+   dim3 bs( 32, 4, 2 );
+   dim3 gs( ( b.ni - 4 + bs.x - 1 ) / bs.x, ( b.nj - 4 + bs.y - 1 ) / bs.y, ( k_hi - k_lo + 1 + bs.z - 1 ) / bs.z );
+   if( mode == MODE_LU ) k_rhs_v1<MODE_LU><<<gs, bs, 0, st>>>( a, k_lo, k_hi );
+   else if( mode == MODE_PRED ) k_rhs_v1<MODE_PRED><<<gs, bs, 0, st>>>( a, k_lo, k_hi );
+   else k_rhs_v1<MODE_CORR><<<gs, bs, 0, st>>>( a, k_lo, k_hi );
+   count_launch();
+   return check_launch( "k_rhs_v1" );
+}
+
+// closure rows only (used next to the fast interior kernel): rows [k_lo,k_hi]
+int launch_rhs_v1_rows( RhsMode mode, const RhsArgs& a, int k_lo, int k_hi, cudaStream_t st )
+{
+   const Block& b = a.b;
+   if( k_hi < k_lo ) return 0;
+   dim3 bs( 32, 4, 2 );
+   dim3 gs( ( b.ni - 4 + bs.x - 1 ) / bs.x, ( b.nj - 4 + bs.y - 1 ) / bs.y, ( k_hi - k_lo + 1 + bs.z - 1 ) / bs.z );
+   if( mode == MODE_LU ) k_rhs_v1<MODE_LU><<<gs, bs, 0, st>>>( a, k_lo, k_hi );
+   else if( mode == MODE_PRED ) k_rhs_v1<MODE_PRED><<<gs, bs, 0, st>>>( a, k_lo, k_hi );
+   else k_rhs_v1<MODE_CORR><<<gs, bs, 0, st>>>( a, k_lo, k_hi );
+   count_launch();
+   return check_launch( "k_rhs_v1_rows" );
+}
+
+int launch_shell_update( RhsMode mode, const RhsArgs& a, cudaStream_t st )
+{
+   const Block& b = a.b;
+   const long long total = 2 * ( 2 * b.nij + 2LL * b.ni * ( b.nk - 4 ) + 2LL * ( b.nj - 4 ) * ( b.nk - 4 ) );
+   if( mode == MODE_PRED ) k_shell_update<MODE_PRED><<<nblocks( total, 256 ), 256, 0, st>>>( a );
+   else k_shell_update<MODE_CORR><<<nblocks( total, 256 ), 256, 0, st>>>( a );
+   count_launch();
+   return check_launch( "k_shell_update" );
+}
+
+int launch_predfort( const Block& b, double* up, const double* u, const double* um, const double* lu,
+		     const double* fo, const double* rho, double dt2, cudaStream_t st )
+{
+   k_predfort<<<nblocks( b.npts, 256 ), 256, 0, st>>>( b, up, u, um, lu, fo, rho, dt2 );
+   count_launch();
+   return check_launch( "k_predfort" );
+}
+int launch_corrfort( const Block& b, double* up, const double* lu, const double* fo, const double* rho,
+		     double dt4, cudaStream_t st )
+{
+   k_corrfort<<<nblocks( b.npts, 256 ), 256, 0, st>>>( b, up, lu, fo, rho, dt4 / 12 );
+   count_launch();
+   return check_launch( "k_corrfort" );
+}
+int launch_dpdmt( long long n, const double* up, const double* u, const double* um, double* u2, double dt2i,
+		  cudaStream_t st )
+{
+   k_dpdmt<<<nblocks( n, 256 ), 256, 0, st>>>( n, up, u, um, u2, dt2i );
+   count_launch();
+   return check_launch( "k_dpdmt" );
+}
+int launch_addsgd( int order, const Block& b, double* up, const double* u, const double* um, const double* rho,
+		   const double* dcx, const double* dcy, const double* dcz, const double* strx,
+		   const double* stry, const double* strz, const double* cox, const double* coy,
+		   const double* coz, double beta, cudaStream_t st )
+{
+   if( beta == 0 ) return 0;
+   const int w = order == 6 ? 3 : 2;
+   if( b.ni <= 2 * w || b.nj <= 2 * w || b.nk <= 2 * w ) return 0;
+   dim3 bs( 32, 4, 2 );
+   dim3 gs( ( b.ni - 2 * w + bs.x - 1 ) / bs.x, ( b.nj - 2 * w + bs.y - 1 ) / bs.y, ( b.nk - 2 * w + bs.z - 1 ) / bs.z );
+   k_addsgd<<<gs, bs, 0, st>>>( order, b, up, u, um, rho, dcx, dcy, dcz, strx, stry, strz, cox, coy, coz, beta );
+   count_launch();
+   return check_launch( "k_addsgd" );
+}
+
+int launch_bcfortsg( const Block& b, const Int36& wind, int nx, int ny, int nz, double* u, double h,
+		     const Int6& bccnd, const double* mu, const double* la, const Ptr6& bforce,
+		     const double* strx, const double* stry, cudaStream_t st )
+{
+   for( int s = 0; s < 6; s++ )
+   {
+      const int* w = wind.v + 6 * s;
+      const int type = bccnd.v[s];
+      if( type == 1 || type == 2 || type == 3 )
+      {
+	 const long long total = (long long)( w[1] - w[0] + 1 ) * ( w[3] - w[2] + 1 ) * ( w[5] - w[4] + 1 );
+	 if( total <= 0 ) continue;
+	 if( type != 3 && bforce.p[s] == 0 )
+	    return set_error( "bcfortsg: side %d needs a forcing array", s );
+	 long long off = 0;
+	 if( type == 3 )
+	    off = s == 0 ? nx : ( s == 1 ? -nx : ( s == 2 ? (long long)b.ni * ny : ( s == 3 ? -(long long)b.ni * ny
+				 : ( s == 4 ? b.nij * nz : -b.nij * nz ) ) ) );
+	 k_bc_window<<<nblocks( total, 256 ), 256, 0, st>>>( b, s, w[0], w[1], w[2], w[3], w[4], w[5], type, off, u,
+							      bforce.p[s] );
+	 count_launch();
+      }
+      else if( type == 0 )
+      {
+	 if( s != 4 && s != 5 )
+	    return set_error( "bcfortsg: free surface condition not implemented for side %d", s );
+	 if( b.ni < 5 || b.nj < 5 ) continue;
+	 dim3 bs( 32, 8 );
+	 dim3 gs( ( b.ni - 4 + 31 ) / 32, ( b.nj - 4 + 7 ) / 8 );
+	 k_bc_freesurface<<<gs, bs, 0, st>>>( b, s == 4 ? 1 : nz, s == 4 ? 1 : -1, h, u, mu, la, bforce.p[s], strx, stry );
+	 count_launch();
+      }
+   }
+   return check_launch( "bcfortsg" );
+}
+
+int launch_add_point_forces( int corder, long long npts, double* up, const double* rho, int n,
+			     const long long* pidx_, const double* f, double factor, cudaStream_t st )
+{
+   if( n <= 0 ) return 0;
+   k_add_point_forces<<<( n + 127 ) / 128, 128, 0, st>>>( corder ? npts : 1, corder ? 1 : 3, up, rho, n, pidx_, f, factor );
+   count_launch();
+   return check_launch( "k_add_point_forces" );
+}
+int launch_gather_points( int corder, long long npts, const double* u, int n, const long long* pidx_,
+			  double* out, cudaStream_t st )
+{
+   if( n <= 0 ) return 0;
+   k_gather_points<<<( n + 127 ) / 128, 128, 0, st>>>( corder ? npts : 1, corder ? 1 : 3, u, n, pidx_, out );
+   count_launch();
+   return check_launch( "k_gather_points" );
+}
+int launch_halo_copy( const Block& b, double* field, int kplane, double* buf, int pack, cudaStream_t st )
+{
+   k_halo_copy<<<nblocks( 6 * b.nij, 256 ), 256, 0, st>>>( b, field, kplane, buf, pack );
+   count_launch();
+   return check_launch( "k_halo_copy" );
+}
+
+} // namespace sw4b200

@@ -1,0 +1,109 @@
+// Shared declarations of the sw4b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace sw4b200 {
+
+// SBP closure tables, device constant memory (reference: device-routines.C:41-44 dev_acof...).
+// acof(k,q,m) = c_acof[(k-1)+6*(q-1)+48*(m-1)], bope(k,q) = c_bope[(k-1)+6*(q-1)].
+// The library is built as ONE translation unit (sw4b200.cu includes every .cu), so these are
+// plain definitions.
+__constant__ double c_acof[384];
+__constant__ double c_bope[48];
+__constant__ double c_ghcof[6];
+__constant__ double c_sbop[5];
+
+// Geometry of one block in the reference's index convention (bounds include ghost points).
+struct Block
+{
+   int ifirst, ilast, jfirst, jlast, kfirst, klast;
+   int ni, nj, nk;	 // allocated extents
+   long long nij, npts;	 // plane size, block size
+   long long sc, sp;	 // component stride, point stride (corder=1: npts,1 ; corder=0: 1,3)
+};
+
+inline Block make_block( int corder, int ifirst, int ilast, int jfirst, int jlast, int kfirst, int klast )
+{
+   Block b;
+   b.ifirst = ifirst; b.ilast = ilast; b.jfirst = jfirst; b.jlast = jlast; b.kfirst = kfirst; b.klast = klast;
+   b.ni = ilast - ifirst + 1; b.nj = jlast - jfirst + 1; b.nk = klast - kfirst + 1;
+   b.nij = (long long)b.ni * b.nj;
+   b.npts = b.nij * b.nk;
+   if( corder ) { b.sc = b.npts; b.sp = 1; }
+   else         { b.sc = 1;      b.sp = 3; }
+   return b;
+}
+
+__host__ __device__ inline long long pidx( const Block& b, int i, int j, int k )
+{
+   return (long long)(i - b.ifirst) + (long long)b.ni * (j - b.jfirst) + b.nij * (k - b.kfirst);
+}
+
+struct Int6 { int v[6]; };
+struct Int36 { int v[36]; };
+struct Ptr6 { const double* p[6]; };
+
+// error plumbing (api.cu)
+int set_error( const char* fmt, ... );
+int check_launch( const char* what );
+void count_launch( int n = 1 );
+cudaStream_t as_stream( void* s );
+
+// ---- launch wrappers implemented in the .cu files -------------------------------------------
+enum RhsMode { MODE_LU = 0, MODE_PRED = 1, MODE_CORR = 2 };
+
+struct RhsArgs
+{
+   Block b;
+   int nk;	    // global interior size in k
+   int onesided4, onesided5;
+   double* out;	    // lu (MODE_LU) or up_out (PRED/CORR)
+   const double *u, *um, *up; // PRED: u,um ; CORR: up,u,um (uacc formed on the fly); LU: u
+   const double *mu, *la, *rho, *fo;
+   const double *strx, *stry, *strz;
+   double h, dt;
+   // supergrid damping fused into MODE_CORR when sg_order != 0
+   const double *dcx, *dcy, *dcz, *cox, *coy, *coz;
+   double beta;
+   int sg_order;
+};
+
+int launch_rhs_v1( RhsMode mode, const RhsArgs& a, cudaStream_t st );
+int launch_rhs_fast( RhsMode mode, const RhsArgs& a, cudaStream_t st ); // optimized SoA path (rhs4sg_fast.cu)
+int launch_shell_update( RhsMode mode, const RhsArgs& a, cudaStream_t st );
+
+int launch_predfort( const Block& b, double* up, const double* u, const double* um, const double* lu,
+		     const double* fo, const double* rho, double dt2, cudaStream_t st );
+int launch_corrfort( const Block& b, double* up, const double* lu, const double* fo, const double* rho,
+		     double dt4, cudaStream_t st );
+int launch_dpdmt( long long n, const double* up, const double* u, const double* um, double* u2, double dt2i,
+		  cudaStream_t st );
+int launch_addsgd( int order, const Block& b, double* up, const double* u, const double* um, const double* rho,
+		   const double* dcx, const double* dcy, const double* dcz,
+		   const double* strx, const double* stry, const double* strz,
+		   const double* cox, const double* coy, const double* coz, double beta, cudaStream_t st );
+int launch_bcfortsg( const Block& b, const Int36& wind, int nx, int ny, int nz, double* u, double h,
+		     const Int6& bccnd, const double* mu, const double* la, const Ptr6& bforce,
+		     const double* strx, const double* stry, cudaStream_t st );
+int launch_add_point_forces( int corder, long long npts, double* up, const double* rho, int n,
+			     const long long* pidx, const double* f, double factor, cudaStream_t st );
+int launch_gather_points( int corder, long long npts, const double* u, int n, const long long* pidx,
+			  double* out, cudaStream_t st );
+int launch_halo_copy( const Block& b, double* field, int kplane, double* buf, int pack, cudaStream_t st );
+
+// curvilinear (curvilinear.cu)
+int launch_rhs4sgcurv( const Block& b, const double* u, const double* mu, const double* la, const double* met,
+		       const double* jac, double* lu, int onesided4, const double* strx, const double* stry,
+		       cudaStream_t st );
+int launch_addsgdc( int order, const Block& b, double* up, const double* u, const double* um, const double* rho,
+		    const double* dcx, const double* dcy, const double* strx, const double* stry,
+		    const double* jac, const double* cox, const double* coy, double beta, cudaStream_t st );
+int launch_freesurfcurvisg( const Block& b, int nz, int side, double* u, const double* mu, const double* la,
+			    const double* met, const double* forcing, const double* strx, const double* stry,
+			    cudaStream_t st );
+int launch_enforce_cart_topo( int corder, double* ucart, const Block& bc, double* ucurv, const Block& bt,
+			      cudaStream_t st );
+
+} // namespace sw4b200

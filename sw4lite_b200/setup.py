@@ -1,0 +1,112 @@
+"""Problem setup for synthetic runs (bench.py, smoke, examples): what the reference's host code
+(parser + setupRun, EW.C:1865-2146, 4636-4868, 5041-5146; SuperGrid.C:108-198) hands to the time
+loop, restated for Cartesian single-grid problems.  Host-side numpy only; nothing here is on the
+hot path.  Parity of these arrays with the reference is checked in tests/test_setup.py."""
+import numpy as np
+
+from .solver import bStressFree, bSuperGrid, boundary_windows
+
+
+def _psi0(xi):
+    """C5 polynomial taper, SuperGrid::Psi0 (SuperGrid.C:170-192)"""
+    xi = np.asarray(xi, dtype=np.float64)
+    f = xi ** 6 * (462 - 1980 * xi + 3465 * xi ** 2 - 3080 * xi ** 3 + 1386 * xi ** 4 - 252 * xi ** 5)
+    return np.where(xi <= 0, 0.0, np.where(xi >= 1, 1.0, f))
+
+
+def supergrid_1d(x, left, right, x0, x1, width, epsL=1e-4, cmin=0.33):
+    """(dc, str, corner) at coordinates x: SuperGrid::dampingCoeff / stretching / cornerTaper
+    (SuperGrid.C:108-198) with trans_width = width/2."""
+    x = np.asarray(x, dtype=np.float64)
+    tw = 0.5 * width
+    psi = np.zeros_like(x); damp = np.zeros_like(x); lin = np.zeros_like(x)
+    if left:
+        m = x < x0 + width
+        psi = np.where(m, _psi0((x0 + width - x) / width), psi)
+        damp = np.where(m, _psi0((x0 + width - x) / tw), damp)
+        lin = np.where(m, (x0 + width - x) / width, lin)
+    if right:
+        m = (x > x1 - width) & ~((x < x0 + width) if left else np.zeros_like(x, dtype=bool))
+        psi = np.where(m, _psi0((x - (x1 - width)) / width), psi)
+        damp = np.where(m, _psi0((x - (x1 - width)) / tw), damp)
+        lin = np.where(m, (x - (x1 - width)) / width, lin)
+    stretch = 1 - (1 - epsL) * psi
+    return damp / stretch, stretch, 1.0 - (1.0 - cmin) * lin
+
+
+def c6smoothbump(freq, t):
+    x = t * freq
+    return np.where((x < 0) | (x > 1), 0.0, 51480 * (x * (1 - x)) ** 7)
+
+
+def c6smoothbump_tt(freq, t):
+    x = t * freq
+    v = 51480 * freq * freq * 7 * (6 * (1 - 2 * x) ** 2 * (x * (1 - x)) ** 5 - 2 * (x * (1 - x)) ** 6)
+    return np.where((x < 0) | (x > 1), 0.0, v)
+
+
+class CartesianProblem:
+    """A single Cartesian grid: free surface on top (k=1), supergrid layers on the other five
+    sides (the reference's default_bcs, EW.C:6077-6082, + `supergrid gp=`), uniform or layered
+    material, point forces with a C6SmoothBump time function."""
+
+    def __init__(self, nx, ny, nz, h, vp=4000.0, vs=2000.0, rho=2600.0, gp=30, cfl=1.3, beta=0.02, corder=1,
+                 free_surface=True, layers=None):
+        self.nx, self.ny, self.nz, self.h = nx, ny, nz, float(h)
+        self.corder = corder
+        self.bounds = (-1, nx + 2, -1, ny + 2, -1, nz + 2)
+        self.ni, self.nj, self.nk = nx + 4, ny + 4, nz + 4
+        self.npts = self.ni * self.nj * self.nk
+        self.bctype = [bSuperGrid] * 6
+        if free_surface:
+            self.bctype[4] = bStressFree
+        self.onesided = [0, 0, 0, 0, 1 if free_surface else 0, 0]
+        self.wind = boundary_windows(self.bounds, self.bctype)
+        self.beta = beta
+        self.gp = gp
+        # material (ghost points get the same constant; `layers` = [(z_top, vp, vs, rho), ...])
+        z = (np.arange(-1, nz + 3) - 1) * self.h
+        vpk = np.full(self.nk, float(vp)); vsk = np.full(self.nk, float(vs)); rhk = np.full(self.nk, float(rho))
+        for (ztop, lvp, lvs, lrho) in (layers or []):
+            m = z >= ztop
+            vpk[m], vsk[m], rhk[m] = lvp, lvs, lrho
+        muk = rhk * vsk ** 2
+        lak = rhk * vpk ** 2 - 2 * muk
+        plane = np.ones(self.ni * self.nj)
+        self.mu = np.repeat(muk, self.ni * self.nj) * np.tile(plane, self.nk)
+        self.la = np.repeat(lak, self.ni * self.nj) * np.tile(plane, self.nk)
+        self.rho = np.repeat(rhk, self.ni * self.nj) * np.tile(plane, self.nk)
+        # supergrid 1-D arrays (EW::assign_supergrid_damping_arrays, EW.C:4671-4801)
+        width = gp * self.h
+        xs = (np.arange(-1, nx + 3) - 1) * self.h
+        ys = (np.arange(-1, ny + 3) - 1) * self.h
+        self.dcx, self.strx, self.cox = supergrid_1d(xs, True, True, 0.0, (nx - 1) * self.h, width)
+        self.dcy, self.stry, self.coy = supergrid_1d(ys, True, True, 0.0, (ny - 1) * self.h, width)
+        self.dcz, self.strz, self.coz = supergrid_1d(z, not free_surface, True, 0.0, (nz - 1) * self.h, width)
+        # time step (EW::computeDT, EW.C:5041-5066): dt = cfl*h/sqrt(max (4mu+la)/rho)
+        self.dt = cfl * self.h / np.sqrt(np.max((4 * muk + lak) / rhk))
+        self.sources = []  # (i,j,k, fx,fy,fz, freq, t0)
+
+    def add_point_force(self, i, j, k, f, freq, t0=0.0):
+        self.sources.append((int(i), int(j), int(k), float(f[0]), float(f[1]), float(f[2]), float(freq), float(t0)))
+
+    def source_points(self):
+        return np.array([[s[0], s[1], s[2]] for s in self.sources], dtype=np.int32).reshape(-1, 3)
+
+    def forces(self, t, tt=False):
+        out = np.zeros((len(self.sources), 3))
+        for n, s in enumerate(self.sources):
+            g = (c6smoothbump_tt if tt else c6smoothbump)(s[6], t - s[7])
+            out[n] = np.array(s[3:6]) * g
+        return out
+
+    def make_block(self, device=0):
+        from .solver import GridBlock
+        g = GridBlock(self.corder, self.bounds, (self.nx, self.ny, self.nz), self.h, self.dt, self.onesided,
+                      self.bctype, self.wind, sg_order=4, beta=self.beta, device=device)
+        for name in ("mu", "rho", "strx", "stry", "strz", "dcx", "dcy", "dcz", "cox", "coy", "coz"):
+            g.upload(name, getattr(self, name))
+        g.upload("lambda", self.la)
+        if self.sources:
+            g.set_source_points(self.source_points())
+        return g
