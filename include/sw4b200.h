@@ -42,6 +42,12 @@ void* sw4b200_stream( int st );            /* cudaStream_t of library stream st 
 int sw4b200_sync_stream( int st );
 int sw4b200_sync_device( void );
 int sw4b200_kernel_launch_count( void );   /* number of kernels launched by this library so far */
+/* per-kernel device time, measured with CUDA events on the launching stream (the timing hooks of
+ * EW::timesteploop's time_measure[], EW.C:2529-2873, at kernel granularity).  Names: "rhs_fast_pred",
+ * "rhs_fast_corr", "rhs_fast_lu", "rhs_v1", "addsgd", "shell", "bc". */
+int sw4b200_profile_enable( int on );
+int sw4b200_profile_reset( void );
+int sw4b200_profile_read( const char* kernel, double* ms_total, long long* launches );
 
 /* ---------------------------------------------------------------- memory
  * replaces Sarray::allocate_on_device / copy_to_device / copy_from_device / page_lock
@@ -216,6 +222,25 @@ int sw4b200_grid_cycle( sw4b200_grid* g );                             /* EW.C:3
 int sw4b200_grid_record( sw4b200_grid* g, double* h_out /*3*nrec*/ );  /* receivers from Up, EW.C:2802-2835 */
 /* all of the above for a single block with no neighbours: one full time step */
 int sw4b200_grid_step( sw4b200_grid* g, const double* h_f, const double* h_ftt, double* h_rec );
+/* phase-split variants for z-slab runs, where the caller exchanges halo planes while the bulk of
+ * the block is still being computed (the boundary/centre split of RHSPredCU_boundary/_center,
+ * EW_cuda.C:1228-1410, applied to z faces).  part 0 = whole block, 1 = only the two interior
+ * planes next to every halo face (what a neighbour slab needs) plus the ghost shell, 2 = the rest
+ * (+ source injection, + supergrid damping for the corrector). */
+int sw4b200_grid_predictor_part( sw4b200_grid* g, int part, const double* h_f );
+int sw4b200_grid_corrector_part( sw4b200_grid* g, int part, const double* h_ftt );
+/* device-resident stepping: the source amplitudes of steps [0,nsteps) (nsteps x 3*nsrc values, F and
+ * F_tt) are uploaded once; sw4b200_grid_run advances nsteps time steps without any host
+ * synchronisation and keeps the receiver samples on the device until they are fetched
+ * (replaces the per-step blocking copy of extractRecordDataCU, EW_cuda.C:2198). */
+int sw4b200_grid_set_source_series( sw4b200_grid* g, int nsteps, const double* h_f, const double* h_ftt );
+int sw4b200_grid_run( sw4b200_grid* g, int first_step, int nsteps );
+int sw4b200_grid_fetch_records( sw4b200_grid* g, int first_step, int nsteps, double* h_out /* nsteps*3*nrec */ );
+/* layered media: fill scalar field `name` ("mu","lambda","rho") with h_kvalues[k-kfirst] on plane k
+ * (what MaterialBlock produces for depth-only blocks, MaterialBlock.C) without a host copy of the field */
+int sw4b200_grid_fill_profile( sw4b200_grid* g, const char* name, const double* h_kvalues /* nk */ );
+/* run this block's kernels on library stream st (0..3) */
+int sw4b200_grid_set_stream( sw4b200_grid* g, int st );
 /* z-slab halo planes of Up: copy the 2 interior planes next to the low (side=0) / high (side=1)
  * face into d_dst (3*2*ni*nj doubles, component-major), or from d_src into the 2 halo planes. */
 int sw4b200_grid_pack_halo( sw4b200_grid* g, int side, double* d_dst, void* stream );

@@ -73,12 +73,153 @@ static bool use_fast_path()
    return v == 1;
 }
 
-// one fused pass over a block: interior rows (fast SoA kernel when possible), closure rows and shell
-static int run_rhs( RhsMode mode, const RhsArgs& a, int corder, cudaStream_t st )
+// ---- optional per-kernel timing
+struct ProfRec { int name; cudaEvent_t e0, e1; };
+static bool g_prof_on = false;
+static std::vector<std::string> g_prof_names;
+static std::vector<ProfRec> g_prof_recs;
+static std::map<std::string, std::pair<double, long long>> g_prof_acc;
+
+ProfScope::ProfScope( const char* name, cudaStream_t st_ ) : slot( -1 ), st( st_ )
 {
+   if( !g_prof_on ) return;
+   int id = -1;
+   for( size_t n = 0; n < g_prof_names.size(); n++ )
+      if( g_prof_names[n] == name ) id = (int)n;
+   if( id < 0 ) { g_prof_names.push_back( name ); id = (int)g_prof_names.size() - 1; }
+   ProfRec r;
+   r.name = id;
+   cudaEventCreate( &r.e0 );
+   cudaEventCreate( &r.e1 );
+   cudaEventRecord( r.e0, st );
+   g_prof_recs.push_back( r );
+   slot = (int)g_prof_recs.size() - 1;
+}
+ProfScope::~ProfScope()
+{
+   if( slot >= 0 ) cudaEventRecord( g_prof_recs[slot].e1, st );
+}
+static void prof_collect()
+{
+   for( ProfRec& r : g_prof_recs )
+   {
+      cudaEventSynchronize( r.e1 );
+      float ms = 0;
+      if( cudaEventElapsedTime( &ms, r.e0, r.e1 ) == cudaSuccess )
+      {
+	 auto& acc = g_prof_acc[g_prof_names[r.name]];
+	 acc.first += ms;
+	 acc.second += 1;
+      }
+      cudaEventDestroy( r.e0 );
+      cudaEventDestroy( r.e1 );
+   }
+   g_prof_recs.clear();
+}
+
+// rows of the block handled by the fast interior kernel (the SBP closure rows go to the general kernel)
+static void fast_rows( const RhsArgs& a, int& klo, int& khi )
+{
+   klo = a.onesided4 ? 7 : a.b.kfirst + 2;
+   khi = a.onesided5 ? a.nk - 6 : a.b.klast - 2;
+   if( klo < a.b.kfirst + 2 ) klo = a.b.kfirst + 2;
+   if( khi > a.b.klast - 2 ) khi = a.b.klast - 2;
+}
+
+static void fast_args( const RhsArgs& a, FastArgs& f )
+{
+   memset( &f, 0, sizeof( f ) );
+   f.b = a.b;
+   for( int c = 0; c < 3; c++ ) f.u[c] = a.u + c * a.b.npts;
+   f.mu = a.mu; f.la = a.la; f.strx = a.strx; f.stry = a.stry; f.strz = a.strz;
+   f.cof = 1.0 / ( a.h * a.h );
+   f.rho = a.rho;
+   for( int c = 0; c < 3; c++ )
+   {
+      f.out[c] = a.out + c * a.b.npts;
+      f.fo[c] = a.fo ? a.fo + c * a.b.npts : 0;
+   }
+}
+
+// scratch array for the API-level corrector (uacc of the whole block)
+static double* g_scratch = 0;
+static size_t g_scratch_cap = 0;
+static double* scratch( size_t doubles )
+{
+   if( doubles > g_scratch_cap )
+   {
+      if( g_scratch ) cudaFree( g_scratch );
+      g_scratch = 0; g_scratch_cap = 0;
+      if( cudaMalloc( (void**)&g_scratch, doubles * sizeof( double ) ) != cudaSuccess )
+      {
+	 set_error( "cannot allocate %zu bytes of scratch", doubles * sizeof( double ) );
+	 return 0;
+      }
+      g_scratch_cap = doubles;
+   }
+   return g_scratch;
+}
+
+// L(u) rows [r0,r1] by the fast kernel where possible and the general kernel on closure rows.
+// mode: MODE_LU, MODE_PRED (a.out2 optional) or MODE_CORR_ACC (a.u = uacc array, a.up = value to correct)
+static int rhs_rows_soa( RhsMode mode, const RhsArgs& a, int r0, int r1, cudaStream_t st )
+{
+   int klo, khi;
+   fast_rows( a, klo, khi );
+   const int f0 = klo > r0 ? klo : r0, f1 = khi < r1 ? khi : r1;
+   if( f1 >= f0 )
+   {
+      FastArgs f;
+      fast_args( a, f );
+      f.klo = f0; f.khi = f1; f.kchunk = 0;
+      int epi = EPI_LU;
+      if( mode == MODE_PRED )
+      {
+	 epi = EPI_PRED;
+	 f.fac = a.dt * a.dt;
+	 for( int c = 0; c < 3; c++ ) { f.um[c] = a.um + c * a.b.npts; f.out2[c] = a.out2 ? a.out2 + c * a.b.npts : 0; }
+      }
+      else if( mode == MODE_CORR_ACC )
+      {
+	 epi = EPI_CORR;
+	 const double dt2 = a.dt * a.dt;
+	 f.fac = dt2 * dt2 / 12;
+	 for( int c = 0; c < 3; c++ ) f.um[c] = a.up + c * a.b.npts;
+      }
+      if( launch_fast( epi, f, st ) ) return 1;
+      // closure rows below and above the fast rows
+      if( r0 < f0 && launch_rhs_v1_rows( mode, a, r0, f0 - 1, st ) ) return 1;
+      if( r1 > f1 && launch_rhs_v1_rows( mode, a, f1 + 1, r1, st ) ) return 1;
+      return 0;
+   }
+   return launch_rhs_v1_rows( mode, a, r0, r1, st );
+}
+
+// one fused pass over a whole block through the operator-level API
+static int run_rhs( RhsMode mode, const RhsArgs& a_in, int corder, cudaStream_t st )
+{
+   RhsArgs a = a_in;
+   const int r0 = a.b.kfirst + 2, r1 = a.b.klast - 2;
    int rc;
-   if( corder && use_fast_path() )
-      rc = launch_rhs_fast( mode, a, st );
+   if( corder && use_fast_path() && a.b.ni >= 5 && a.b.nj >= 5 )
+   {
+      if( mode == MODE_CORR )
+      {
+	 // uacc of the whole block, then corrector (out of place) and supergrid damping
+	 double* ua = scratch( 3 * (size_t)a.b.npts );
+	 if( !ua ) return 1;
+	 if( launch_dpdmt( 3 * a.b.npts, a.up, a.u, a.um, ua, 1.0 / ( a.dt * a.dt ), st ) ) return 1;
+	 RhsArgs c = a;
+	 c.u = ua;
+	 if( rhs_rows_soa( MODE_CORR_ACC, c, r0, r1, st ) ) return 1;
+	 if( launch_shell_update( MODE_CORR, a, st ) ) return 1;
+	 if( a.sg_order )
+	    return launch_addsgd( a.sg_order, a.b, a.out, a.u, a.um, a.rho, a.dcx, a.dcy, a.dcz, a.strx, a.stry, a.strz,
+				  a.cox, a.coy, a.coz, a.beta, st );
+	 return 0;
+      }
+      rc = rhs_rows_soa( mode, a, r0, r1, st );
+   }
    else
       rc = launch_rhs_v1( mode, a, st );
    if( rc ) return rc;
@@ -95,8 +236,17 @@ struct sw4b200_grid
    sw4b200_grid_desc d;
    Block b;
    cudaStream_t st;
-   double *U, *Um, *Up, *Up2;
+   double *U, *Um, *Up, *Uacc; // Uacc: stored acceleration (SoA fast path) / second Up buffer (general path)
    double *mu, *la, *rho, *jac, *met;
+   bool fast;		       // SoA Cartesian throughput path
+   std::vector<double>* h_dc[3]; // host copies of the damping arrays -> boxes where the damping is non-zero
+   std::vector<Int6>* sgd_boxes;
+   bool sgd_boxes_valid;
+   // device-resident source amplitude tables and receiver records for sw4b200_grid_run
+   int series_steps;
+   double *d_fser, *d_fttser;
+   double* d_recser;
+   int recser_steps;
    double *str[3], *dc[3], *co[3];
    double* bforce[6];
    size_t nbf[6];
@@ -450,7 +600,10 @@ sw4b200_grid* sw4b200_grid_create( const sw4b200_grid_desc* desc )
    g->b = make_block( desc->corder, desc->ifirst, desc->ilast, desc->jfirst, desc->jlast, desc->kfirst, desc->klast );
    g->st = g_streams[0];
    const size_t np = (size_t)g->b.npts;
-   double** three[4] = { &g->U, &g->Um, &g->Up, &g->Up2 };
+   g->fast = desc->corder == 1 && !desc->curvilinear && use_fast_path();
+   for( int d = 0; d < 3; d++ ) g->h_dc[d] = new std::vector<double>();
+   g->sgd_boxes = new std::vector<Int6>();
+   double** three[4] = { &g->U, &g->Um, &g->Up, &g->Uacc };
    for( int a = 0; a < 4; a++ )
    {
       *three[a] = (double*)sw4b200_malloc( 3 * np * 8 );
@@ -503,8 +656,10 @@ int sw4b200_grid_destroy( sw4b200_grid* g )
 {
    if( !g ) return 0;
    cudaStreamSynchronize( g->st );
-   double* ptrs[] = { g->U, g->Um, g->Up, g->Up2, g->mu, g->la, g->rho, g->jac, g->met, g->d_f, g->d_rec,
-		      g->halo_buf[0], g->halo_buf[1] };
+   double* ptrs[] = { g->U, g->Um, g->Up, g->Uacc, g->mu, g->la, g->rho, g->jac, g->met, g->d_f, g->d_rec,
+		      g->halo_buf[0], g->halo_buf[1], g->d_fser, g->d_fttser, g->d_recser };
+   for( int d = 0; d < 3; d++ ) delete g->h_dc[d];
+   delete g->sgd_boxes;
    for( double* p : ptrs ) if( p ) cudaFree( p );
    for( int d = 0; d < 3; d++ ) { cudaFree( g->str[d] ); cudaFree( g->dc[d] ); cudaFree( g->co[d] ); }
    for( int s = 0; s < 6; s++ ) if( g->bforce[s] ) cudaFree( g->bforce[s] );
@@ -523,6 +678,12 @@ int sw4b200_grid_upload( sw4b200_grid* g, const char* name, const double* h_src 
    if( !p || !*p ) return set_error( "grid_upload: unknown or unallocated array '%s'", name );
    CUDA_OK( cudaMemcpyAsync( *p, h_src, n * 8, cudaMemcpyHostToDevice, g->st ) );
    CUDA_OK( cudaStreamSynchronize( g->st ) );
+   for( int d = 0; d < 3; d++ )
+      if( p == &g->dc[d] )
+      {
+	 g->h_dc[d]->assign( h_src, h_src + n );
+	 g->sgd_boxes_valid = false;
+      }
    return 0;
 }
 int sw4b200_grid_download( sw4b200_grid* g, const char* name, double* h_dst )
@@ -607,27 +768,191 @@ static void fill_args( sw4b200_grid* g, RhsArgs& a )
    a.sg_order = g->d.beta == 0 ? 0 : g->d.sg_order;
 }
 
-static int inject( sw4b200_grid* g, const double* h_f, int slot, double factor )
+// k-ranges (global k, inclusive) of the interior rows that `part` covers: 0 = all, 1 = the two planes
+// next to every halo face, 2 = the rest
+static int part_ranges( sw4b200_grid* g, int part, int r[2][2] )
 {
+   const int r0 = g->b.kfirst + 2, r1 = g->b.klast - 2;
+   const int lo_n = g->d.halo_lo ? 2 : 0, hi_n = g->d.halo_hi ? 2 : 0;
+   if( part == 0 || r1 - r0 + 1 <= lo_n + hi_n )
+   {
+      if( part == 2 ) return 0;
+      r[0][0] = r0; r[0][1] = r1;
+      return 1;
+   }
+   if( part == 2 )
+   {
+      r[0][0] = r0 + lo_n; r[0][1] = r1 - hi_n;
+      return 1;
+   }
+   int n = 0;
+   if( lo_n ) { r[n][0] = r0; r[n][1] = r0 + 1; n++; }
+   if( hi_n ) { r[n][0] = r1 - 1; r[n][1] = r1; n++; }
+   return n;
+}
+
+// add factor/rho * f to Up (and factor2/rho * f to Uacc) at the source points lying in the rows of `part`
+static int inject_dev( sw4b200_grid* g, const double* dp, double factor, bool with_acc, int part )
+{
+   if( g->nsrc == 0 ) return 0;
+   int r[2][2];
+   const int n = part_ranges( g, part, r );
+   for( int m = 0; m < n; m++ )
+      if( launch_add_point_forces( g->d.corder, g->b.npts, g->Up, g->rho, g->nsrc, g->d_srcidx, dp, factor, g->st,
+				   with_acc ? g->Uacc : 0, 1.0, g->b.nij, r[m][0] - g->b.kfirst, r[m][1] - g->b.kfirst ) )
+	 return 1;
+   return 0;
+}
+
+static int upload_forces( sw4b200_grid* g, const double* h_f, int slot, double** dp )
+{
+   *dp = 0;
    if( g->nsrc == 0 || h_f == 0 ) return 0;
    double* hp = g->h_f + slot * 3 * g->nsrc;
-   double* dp = g->d_f + slot * 3 * g->nsrc;
+   *dp = g->d_f + slot * 3 * g->nsrc;
+   // the pinned staging slot may still be in flight from the previous step
+   CUDA_OK( cudaStreamSynchronize( g->st ) );
    memcpy( hp, h_f, 3 * g->nsrc * sizeof( double ) );
-   CUDA_OK( cudaMemcpyAsync( dp, hp, 3 * g->nsrc * sizeof( double ), cudaMemcpyHostToDevice, g->st ) );
-   return launch_add_point_forces( g->d.corder, g->b.npts, g->Up, g->rho, g->nsrc, g->d_srcidx, dp, factor, g->st );
+   CUDA_OK( cudaMemcpyAsync( *dp, hp, 3 * g->nsrc * sizeof( double ), cudaMemcpyHostToDevice, g->st ) );
+   return 0;
 }
 
 static int curv_predictor( sw4b200_grid* g, const double* h_f );
 static int curv_corrector( sw4b200_grid* g, const double* h_ftt );
 
-int sw4b200_grid_predictor( sw4b200_grid* g, const double* h_f )
+// the parts of the predictor / corrector that need no host data
+static int predictor_dev( sw4b200_grid* g, int part )
 {
    RhsArgs a;
    fill_args( g, a );
-   if( g->d.curvilinear ) return curv_predictor( g, h_f );
    a.out = g->Up; a.u = g->U; a.um = g->Um; a.fo = 0;
-   if( run_rhs( MODE_PRED, a, g->d.corder, g->st ) ) return 1;
-   return inject( g, h_f, 0, g->d.dt * g->d.dt );
+   if( !g->fast )
+   {
+      if( part == 2 ) return 0;
+      return run_rhs( MODE_PRED, a, g->d.corder, g->st );
+   }
+   a.out2 = g->Uacc;
+   if( part != 2 && launch_shell_update( MODE_PRED, a, g->st ) ) return 1;
+   int r[2][2];
+   const int n = part_ranges( g, part, r );
+   for( int m = 0; m < n; m++ )
+      if( rhs_rows_soa( MODE_PRED, a, r[m][0], r[m][1], g->st ) ) return 1;
+   return 0;
+}
+
+// boxes (local index ranges) where the supergrid damping update can be non-zero: the x term at i
+// needs dcx(i-hw..i+hw) != 0 etc.; outside them the update subtracts exactly zero.
+static void build_sgd_boxes( sw4b200_grid* g )
+{
+   g->sgd_boxes->clear();
+   const int order = g->d.sg_order;
+   const int w = order == 6 ? 3 : 2, hw = order == 6 ? 2 : 1;
+   const int n[3] = { g->b.ni, g->b.nj, g->b.nk };
+   std::vector<std::pair<int, int>> on[3], off[3];
+   for( int d = 0; d < 3; d++ )
+   {
+      const std::vector<double>& dc = *g->h_dc[d];
+      std::vector<char> act( n[d], 0 );
+      for( int i = w; i <= n[d] - 1 - w; i++ )
+      {
+	 bool nz = dc.size() != (size_t)n[d]; // unknown values: assume active
+	 for( int m = -hw; m <= hw && !nz; m++ ) nz = dc[i + m] != 0;
+	 act[i] = nz;
+      }
+      int i = w;
+      while( i <= n[d] - 1 - w )
+      {
+	 int j = i;
+	 while( j + 1 <= n[d] - 1 - w && act[j + 1] == act[i] ) j++;
+	 ( act[i] ? on[d] : off[d] ).push_back( std::make_pair( i, j ) );
+	 i = j + 1;
+      }
+   }
+   const std::pair<int, int> fx( w, n[0] - 1 - w ), fy( w, n[1] - 1 - w );
+   auto add = [&]( std::pair<int, int> x, std::pair<int, int> y, std::pair<int, int> z ) {
+      Int6 b = { { x.first, x.second, y.first, y.second, z.first, z.second } };
+      g->sgd_boxes->push_back( b );
+   };
+   for( auto& z : on[2] ) add( fx, fy, z );
+   for( auto& z : off[2] )
+   {
+      for( auto& y : on[1] ) add( fx, y, z );
+      for( auto& y : off[1] )
+	 for( auto& x : on[0] ) add( x, y, z );
+   }
+   g->sgd_boxes_valid = true;
+}
+
+static int damping_dev( sw4b200_grid* g, int part )
+{
+   if( g->d.sg_order == 0 || g->d.beta == 0 ) return 0;
+   if( !g->sgd_boxes_valid ) build_sgd_boxes( g );
+   int r[2][2];
+   const int n = part_ranges( g, part, r );
+   for( int m = 0; m < n; m++ )
+      for( const Int6& box0 : *g->sgd_boxes )
+      {
+	 Int6 box = box0;
+	 const int ka = r[m][0] - g->b.kfirst, kb = r[m][1] - g->b.kfirst;
+	 if( box.v[4] < ka ) box.v[4] = ka;
+	 if( box.v[5] > kb ) box.v[5] = kb;
+	 if( box.v[5] < box.v[4] ) continue;
+	 if( launch_addsgd_box( g->d.sg_order, g->b, box, g->Up, g->U, g->Um, g->rho, g->dc[0], g->dc[1], g->dc[2],
+				g->str[0], g->str[1], g->str[2], g->co[0], g->co[1], g->co[2], g->d.beta, g->st ) )
+	    return 1;
+      }
+   return 0;
+}
+
+static int corrector_dev( sw4b200_grid* g, int part )
+{
+   RhsArgs a;
+   fill_args( g, a );
+   if( !g->fast )
+   {
+      if( part == 2 ) return 0;
+      a.out = g->Uacc; a.up = g->Up; a.u = g->U; a.um = g->Um; a.fo = 0;
+      if( run_rhs( MODE_CORR, a, g->d.corder, g->st ) ) return 1;
+      double* t = g->Up; g->Up = g->Uacc; g->Uacc = t;
+      return 0;
+   }
+   if( part != 2 )
+   {
+      // acceleration on the 2-point shell (ghost points, halo planes) from the boundary-conditioned predictor
+      a.out2 = g->Uacc; a.up = g->Up; a.u = g->U; a.um = g->Um;
+      if( launch_shell_update( MODE_SHELL_DPDMT, a, g->st ) ) return 1;
+   }
+   a.out = g->Up; a.up = g->Up; a.u = g->Uacc; a.um = 0; a.out2 = 0; a.fo = 0;
+   int r[2][2];
+   const int n = part_ranges( g, part, r );
+   for( int m = 0; m < n; m++ )
+      if( rhs_rows_soa( MODE_CORR_ACC, a, r[m][0], r[m][1], g->st ) ) return 1;
+   return 0;
+}
+
+// predictor of the rows of `part`: rows, then the sources lying in them
+static int predictor_part( sw4b200_grid* g, int part, const double* d_f )
+{
+   if( predictor_dev( g, part ) ) return 1;
+   if( !g->fast && part != 0 ) return part == 2 ? 0 : ( d_f ? inject_dev( g, d_f, g->d.dt * g->d.dt, false, 0 ) : 0 );
+   return d_f ? inject_dev( g, d_f, g->d.dt * g->d.dt, g->fast, part ) : 0;
+}
+// corrector of the rows of `part`: rows, F_tt at the sources lying in them, supergrid damping
+static int corrector_part( sw4b200_grid* g, int part, const double* d_ftt )
+{
+   const double dt2 = g->d.dt * g->d.dt;
+   if( corrector_dev( g, part ) ) return 1;
+   if( !g->fast && part != 0 ) return part == 2 ? 0 : ( d_ftt ? inject_dev( g, d_ftt, dt2 * dt2 / 12, false, 0 ) : 0 );
+   if( d_ftt && inject_dev( g, d_ftt, dt2 * dt2 / 12, false, part ) ) return 1;
+   return g->fast ? damping_dev( g, part ) : 0;
+}
+
+int sw4b200_grid_predictor( sw4b200_grid* g, const double* h_f )
+{
+   if( g->d.curvilinear ) return curv_predictor( g, h_f );
+   double* d_f;
+   if( upload_forces( g, h_f, 0, &d_f ) ) return 1;
+   return predictor_part( g, 0, d_f );
 }
 
 int sw4b200_grid_enforce_bc( sw4b200_grid* g )
@@ -646,18 +971,14 @@ int sw4b200_grid_enforce_bc( sw4b200_grid* g )
 
 int sw4b200_grid_corrector( sw4b200_grid* g, const double* h_ftt )
 {
-   RhsArgs a;
-   fill_args( g, a );
    if( g->d.curvilinear ) return curv_corrector( g, h_ftt );
-   a.out = g->Up2; a.up = g->Up; a.u = g->U; a.um = g->Um; a.fo = 0;
-   if( run_rhs( MODE_CORR, a, g->d.corder, g->st ) ) return 1;
-   double* t = g->Up; g->Up = g->Up2; g->Up2 = t;
-   const double dt2 = g->d.dt * g->d.dt;
-   return inject( g, h_ftt, 1, dt2 * dt2 / 12 );
+   double* d_ftt;
+   if( upload_forces( g, h_ftt, 1, &d_ftt ) ) return 1;
+   return corrector_part( g, 0, d_ftt );
 }
 
 // curvilinear grid block: unfused sequence rhs4sgcurv -> predictor / dpdmt -> rhs4sgcurv -> corrector
-// -> addsgd4c, with Up2 as the L(u) scratch array (zero on the shell, like the reference's Lu)
+// -> addsgd4c, with Uacc as the scratch array
 static int curv_predictor( sw4b200_grid* g, const double* h_f )
 {
    (void)g; (void)h_f;
@@ -694,6 +1015,130 @@ int sw4b200_grid_step( sw4b200_grid* g, const double* h_f, const double* h_ftt, 
    if( sw4b200_grid_enforce_bc( g ) ) return 1;
    if( h_rec && sw4b200_grid_record( g, h_rec ) ) return 1;
    return sw4b200_grid_cycle( g );
+}
+
+// ---- phase-split entry points for z-slab runs (the caller moves the halo planes between phases)
+int sw4b200_grid_predictor_part( sw4b200_grid* g, int part, const double* h_f )
+{
+   if( g->d.curvilinear ) return part == 2 ? 0 : curv_predictor( g, h_f );
+   if( part < 0 || part > 2 ) return set_error( "predictor_part: part must be 0, 1 or 2" );
+   double* d_f = g->nsrc ? g->d_f : 0;
+   if( part != 2 && upload_forces( g, h_f, 0, &d_f ) ) return 1; // part 2 reuses the values uploaded by part 1
+   if( h_f == 0 ) d_f = 0;
+   return predictor_part( g, part, d_f );
+}
+int sw4b200_grid_corrector_part( sw4b200_grid* g, int part, const double* h_ftt )
+{
+   if( g->d.curvilinear ) return part == 2 ? 0 : curv_corrector( g, h_ftt );
+   if( part < 0 || part > 2 ) return set_error( "corrector_part: part must be 0, 1 or 2" );
+   double* d_ftt = g->nsrc ? g->d_f + 3 * g->nsrc : 0;
+   if( part != 2 && upload_forces( g, h_ftt, 1, &d_ftt ) ) return 1;
+   if( h_ftt == 0 ) d_ftt = 0;
+   return corrector_part( g, part, d_ftt );
+}
+
+// ---- device-resident runs: source amplitudes of all steps uploaded once, receivers kept on the device
+int sw4b200_grid_set_source_series( sw4b200_grid* g, int nsteps, const double* h_f, const double* h_ftt )
+{
+   if( g->d_fser ) { cudaFree( g->d_fser ); g->d_fser = 0; }
+   if( g->d_fttser ) { cudaFree( g->d_fttser ); g->d_fttser = 0; }
+   g->series_steps = 0;
+   if( nsteps <= 0 || g->nsrc == 0 ) return 0;
+   const size_t n = (size_t)nsteps * 3 * g->nsrc * sizeof( double );
+   CUDA_OK( cudaMalloc( (void**)&g->d_fser, n ) );
+   CUDA_OK( cudaMalloc( (void**)&g->d_fttser, n ) );
+   CUDA_OK( cudaMemcpy( g->d_fser, h_f, n, cudaMemcpyHostToDevice ) );
+   CUDA_OK( cudaMemcpy( g->d_fttser, h_ftt, n, cudaMemcpyHostToDevice ) );
+   g->series_steps = nsteps;
+   return 0;
+}
+
+int sw4b200_grid_run( sw4b200_grid* g, int first_step, int nsteps )
+{
+   if( g->d.curvilinear ) return set_error( "grid_run: curvilinear grid blocks are not implemented yet" );
+   if( g->nsrc > 0 && first_step + nsteps > g->series_steps )
+      return set_error( "grid_run: steps [%d,%d) exceed the uploaded source series (%d steps)", first_step,
+			first_step + nsteps, g->series_steps );
+   if( g->nrec > 0 && g->recser_steps < first_step + nsteps )
+   {
+      double* nb = 0;
+      const size_t per = 3 * (size_t)g->nrec;
+      CUDA_OK( cudaMalloc( (void**)&nb, ( size_t )( first_step + nsteps ) * per * sizeof( double ) ) );
+      if( g->d_recser )
+      {
+	 CUDA_OK( cudaMemcpyAsync( nb, g->d_recser, (size_t)g->recser_steps * per * sizeof( double ), cudaMemcpyDeviceToDevice, g->st ) );
+	 CUDA_OK( cudaStreamSynchronize( g->st ) );
+	 cudaFree( g->d_recser );
+      }
+      g->d_recser = nb;
+      g->recser_steps = first_step + nsteps;
+   }
+   for( int s = first_step; s < first_step + nsteps; s++ )
+   {
+      if( predictor_part( g, 0, g->nsrc ? g->d_fser + (size_t)s * 3 * g->nsrc : 0 ) ) return 1;
+      if( sw4b200_grid_enforce_bc( g ) ) return 1;
+      if( corrector_part( g, 0, g->nsrc ? g->d_fttser + (size_t)s * 3 * g->nsrc : 0 ) ) return 1;
+      if( sw4b200_grid_enforce_bc( g ) ) return 1;
+      if( g->nrec && launch_gather_points( g->d.corder, g->b.npts, g->Up, g->nrec, g->d_recidx,
+					   g->d_recser + (size_t)s * 3 * g->nrec, g->st ) )
+	 return 1;
+      sw4b200_grid_cycle( g );
+   }
+   return 0;
+}
+
+int sw4b200_grid_fetch_records( sw4b200_grid* g, int first_step, int nsteps, double* h_out )
+{
+   if( g->nrec == 0 || nsteps <= 0 ) return 0;
+   if( first_step + nsteps > g->recser_steps ) return set_error( "grid_fetch_records: steps not recorded" );
+   CUDA_OK( cudaMemcpyAsync( h_out, g->d_recser + (size_t)first_step * 3 * g->nrec,
+			     (size_t)nsteps * 3 * g->nrec * sizeof( double ), cudaMemcpyDeviceToHost, g->st ) );
+   CUDA_OK( cudaStreamSynchronize( g->st ) );
+   return 0;
+}
+
+// scalar field from a per-plane profile: value[k] for every point of plane k (layered media)
+int sw4b200_grid_fill_profile( sw4b200_grid* g, const char* name, const double* h_kvalues )
+{
+   size_t n = 0;
+   double** p = grid_array( g, name, &n );
+   if( !p || !*p || n != (size_t)g->b.npts ) return set_error( "grid_fill_profile: '%s' is not a scalar field of the block", name );
+   double* d_prof = 0;
+   CUDA_OK( cudaMalloc( (void**)&d_prof, g->b.nk * sizeof( double ) ) );
+   CUDA_OK( cudaMemcpy( d_prof, h_kvalues, g->b.nk * sizeof( double ), cudaMemcpyHostToDevice ) );
+   const int rc = launch_fill_profile( g->b, *p, d_prof, g->st );
+   CUDA_OK( cudaStreamSynchronize( g->st ) );
+   cudaFree( d_prof );
+   return rc;
+}
+
+int sw4b200_grid_set_stream( sw4b200_grid* g, int st )
+{
+   if( st < 0 || st >= 4 ) return set_error( "grid_set_stream: bad stream %d", st );
+   g->st = g_streams[st];
+   return 0;
+}
+
+int sw4b200_profile_enable( int on )
+{
+   if( need_init() ) return 1;
+   if( !on ) prof_collect();
+   g_prof_on = on != 0;
+   return 0;
+}
+int sw4b200_profile_reset( void )
+{
+   prof_collect();
+   g_prof_acc.clear();
+   return 0;
+}
+int sw4b200_profile_read( const char* kernel, double* ms_total, long long* launches )
+{
+   prof_collect();
+   auto it = g_prof_acc.find( kernel );
+   *ms_total = it == g_prof_acc.end() ? 0.0 : it->second.first;
+   *launches = it == g_prof_acc.end() ? 0 : it->second.second;
+   return 0;
 }
 
 int sw4b200_grid_pack_halo( sw4b200_grid* g, int side, double* d_dst, void* stream )

@@ -269,7 +269,22 @@ __global__ void __launch_bounds__( 256 ) k_rhs_v1( RhsArgs a, int k_lo, int k_hi
       {
 	 const long long q = c * b.sc + b.sp * p;
 	 const double fo = a.fo ? a.fo[q] : 0.0;
-	 a.out[q] = 2 * a.u[q] - a.um[q] + f * ( cof * r[c] + fo );
+	 const double acc = cof * r[c] + fo;
+	 a.out[q] = 2 * a.u[q] - a.um[q] + f * acc;
+	 if( a.out2 ) a.out2[q] = acc / a.rho[p];
+      }
+   }
+   else if( MODE == MODE_CORR_ACC )
+   {
+      // field = stored uacc array; in-place correction of up at the own point
+      const double dt2 = a.dt * a.dt;
+      const double f = ( dt2 * dt2 / 12 ) / a.rho[p];
+#pragma unroll
+      for( int c = 0; c < 3; c++ )
+      {
+	 const long long q = c * b.sc + b.sp * p;
+	 const double fo = a.fo ? a.fo[q] : 0.0;
+	 a.out[q] = a.up[q] + f * ( cof * r[c] + fo );
       }
    }
    else
@@ -354,7 +369,17 @@ __global__ void k_shell_update( RhsArgs a )
 	 if( side ) i += b.ni - 2;
       }
       const long long p = (long long)i + (long long)b.ni * j + b.nij * k;
-      if( MODE == MODE_PRED )
+      if( MODE == MODE_SHELL_DPDMT )
+      {
+	 const double dt2i = 1.0 / ( a.dt * a.dt );
+#pragma unroll
+	 for( int c = 0; c < 3; c++ )
+	 {
+	    const long long q = c * b.sc + b.sp * p;
+	    a.out2[q] = dt2i * ( a.up[q] - 2 * a.u[q] + a.um[q] );
+	 }
+      }
+      else if( MODE == MODE_PRED )
       {
 	 const double f = ( a.dt * a.dt ) / a.rho[p];
 #pragma unroll
@@ -421,7 +446,7 @@ __global__ void k_dpdmt( long long n, const double* __restrict__ up, const doubl
       u2[p] = dt2i * ( up[p] - 2 * u[p] + um[p] );
 }
 
-__global__ void k_addsgd( int order, Block b, double* __restrict__ up, const double* __restrict__ u,
+__global__ void k_addsgd( int order, Block b, Int6 box, double* __restrict__ up, const double* __restrict__ u,
 			  const double* __restrict__ um, const double* __restrict__ rho,
 			  const double* __restrict__ dcx, const double* __restrict__ dcy,
 			  const double* __restrict__ dcz, const double* __restrict__ strx,
@@ -429,11 +454,11 @@ __global__ void k_addsgd( int order, Block b, double* __restrict__ up, const dou
 			  const double* __restrict__ cox, const double* __restrict__ coy,
 			  const double* __restrict__ coz, double beta )
 {
-   const int w = order == 6 ? 3 : 2;
-   const int ii = w + blockIdx.x * blockDim.x + threadIdx.x;
-   const int jj = w + blockIdx.y * blockDim.y + threadIdx.y;
-   const int kk = w + blockIdx.z * blockDim.z + threadIdx.z;
-   if( ii > b.ni - 1 - w || jj > b.nj - 1 - w || kk > b.nk - 1 - w ) return;
+   // box = local (array) index ranges, inclusive
+   const int ii = box.v[0] + blockIdx.x * blockDim.x + threadIdx.x;
+   const int jj = box.v[2] + blockIdx.y * blockDim.y + threadIdx.y;
+   const int kk = box.v[4] + blockIdx.z * blockDim.z + threadIdx.z;
+   if( ii > box.v[1] || jj > box.v[3] || kk > box.v[5] ) return;
    const long long p = (long long)ii + (long long)b.ni * jj + b.nij * kk;
    const double prex = strx[ii] * coy[jj] * coz[kk];
    const double prey = stry[jj] * cox[ii] * coz[kk];
@@ -513,14 +538,26 @@ __global__ void k_bc_freesurface( Block b, int k, int kl, double h, double* __re
 
 __global__ void k_add_point_forces( long long sc, long long sp, double* __restrict__ up,
 				    const double* __restrict__ rho, int n, const long long* __restrict__ pidx_,
-				    const double* __restrict__ f, double factor )
+				    const double* __restrict__ f, double factor, double* __restrict__ up2, double factor2,
+				    long long nij, int kplane_lo, int kplane_hi )
 {
    const int t = blockIdx.x * blockDim.x + threadIdx.x;
    if( t >= n ) return;
    const long long p = pidx_[t];
+   if( nij > 0 )
+   {
+      const long long kp = p / nij;
+      if( kp < kplane_lo || kp > kplane_hi ) return;
+   }
    const double s = factor / rho[p];
 #pragma unroll
    for( int c = 0; c < 3; c++ ) up[c * sc + sp * p] += s * f[3 * t + c];
+   if( up2 )
+   {
+      const double s2 = factor2 / rho[p];
+#pragma unroll
+      for( int c = 0; c < 3; c++ ) up2[c * sc + sp * p] += s2 * f[3 * t + c];
+   }
 }
 
 __global__ void k_gather_points( long long sc, long long sp, const double* __restrict__ u, int n,
@@ -550,6 +587,13 @@ __global__ void k_halo_copy( Block b, double* __restrict__ field, int kplane, do
    }
 }
 
+__global__ void k_fill_profile( Block b, double* __restrict__ a, const double* __restrict__ prof )
+{
+   for( long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < b.npts;
+	p += (long long)gridDim.x * blockDim.x )
+      a[p] = prof[p / b.nij];
+}
+
 inline int nblocks( long long n, int bs, int cap = 148 * 16 )
 {
    long long g = ( n + bs - 1 ) / bs;
@@ -560,39 +604,34 @@ inline int nblocks( long long n, int bs, int cap = 148 * 16 )
 
 } // namespace
 
-int launch_rhs_v1( RhsMode mode, const RhsArgs& a, cudaStream_t st )
+// rows [k_lo,k_hi] of the block (interior and/or closure rows)
+int launch_rhs_v1_rows( RhsMode mode, const RhsArgs& a, int k_lo, int k_hi, cudaStream_t st )
 {
    const Block& b = a.b;
-   const int k_lo = b.kfirst + 2, k_hi = b.klast - 2;
    if( k_hi < k_lo || b.ni < 5 || b.nj < 5 ) return 0;
+   ProfScope prof( "rhs_v1", st );
    dim3 bs( 32, 4, 2 );
    dim3 gs( ( b.ni - 4 + bs.x - 1 ) / bs.x, ( b.nj - 4 + bs.y - 1 ) / bs.y, ( k_hi - k_lo + 1 + bs.z - 1 ) / bs.z );
    if( mode == MODE_LU ) k_rhs_v1<MODE_LU><<<gs, bs, 0, st>>>( a, k_lo, k_hi );
    else if( mode == MODE_PRED ) k_rhs_v1<MODE_PRED><<<gs, bs, 0, st>>>( a, k_lo, k_hi );
-   else k_rhs_v1<MODE_CORR><<<gs, bs, 0, st>>>( a, k_lo, k_hi );
+   else if( mode == MODE_CORR ) k_rhs_v1<MODE_CORR><<<gs, bs, 0, st>>>( a, k_lo, k_hi );
+   else k_rhs_v1<MODE_CORR_ACC><<<gs, bs, 0, st>>>( a, k_lo, k_hi );
    count_launch();
    return check_launch( "k_rhs_v1" );
 }
 
-// closure rows only (used next to the fast interior kernel): rows [k_lo,k_hi]
-int launch_rhs_v1_rows( RhsMode mode, const RhsArgs& a, int k_lo, int k_hi, cudaStream_t st )
+int launch_rhs_v1( RhsMode mode, const RhsArgs& a, cudaStream_t st )
 {
-   const Block& b = a.b;
-   if( k_hi < k_lo ) return 0;
-   dim3 bs( 32, 4, 2 );
-   dim3 gs( ( b.ni - 4 + bs.x - 1 ) / bs.x, ( b.nj - 4 + bs.y - 1 ) / bs.y, ( k_hi - k_lo + 1 + bs.z - 1 ) / bs.z );
-   if( mode == MODE_LU ) k_rhs_v1<MODE_LU><<<gs, bs, 0, st>>>( a, k_lo, k_hi );
-   else if( mode == MODE_PRED ) k_rhs_v1<MODE_PRED><<<gs, bs, 0, st>>>( a, k_lo, k_hi );
-   else k_rhs_v1<MODE_CORR><<<gs, bs, 0, st>>>( a, k_lo, k_hi );
-   count_launch();
-   return check_launch( "k_rhs_v1_rows" );
+   return launch_rhs_v1_rows( mode, a, a.b.kfirst + 2, a.b.klast - 2, st );
 }
 
 int launch_shell_update( RhsMode mode, const RhsArgs& a, cudaStream_t st )
 {
    const Block& b = a.b;
    const long long total = 2 * ( 2 * b.nij + 2LL * b.ni * ( b.nk - 4 ) + 2LL * ( b.nj - 4 ) * ( b.nk - 4 ) );
+   ProfScope prof( "shell", st );
    if( mode == MODE_PRED ) k_shell_update<MODE_PRED><<<nblocks( total, 256 ), 256, 0, st>>>( a );
+   else if( mode == MODE_SHELL_DPDMT ) k_shell_update<MODE_SHELL_DPDMT><<<nblocks( total, 256 ), 256, 0, st>>>( a );
    else k_shell_update<MODE_CORR><<<nblocks( total, 256 ), 256, 0, st>>>( a );
    count_launch();
    return check_launch( "k_shell_update" );
@@ -627,9 +666,22 @@ int launch_addsgd( int order, const Block& b, double* up, const double* u, const
    if( beta == 0 ) return 0;
    const int w = order == 6 ? 3 : 2;
    if( b.ni <= 2 * w || b.nj <= 2 * w || b.nk <= 2 * w ) return 0;
+   Int6 box = { { w, b.ni - 1 - w, w, b.nj - 1 - w, w, b.nk - 1 - w } };
+   return launch_addsgd_box( order, b, box, up, u, um, rho, dcx, dcy, dcz, strx, stry, strz, cox, coy, coz, beta, st );
+}
+
+// the same update restricted to a sub-box (local index ranges, inclusive) of the update region
+int launch_addsgd_box( int order, const Block& b, const Int6& box, double* up, const double* u, const double* um,
+		       const double* rho, const double* dcx, const double* dcy, const double* dcz, const double* strx,
+		       const double* stry, const double* strz, const double* cox, const double* coy,
+		       const double* coz, double beta, cudaStream_t st )
+{
+   const int nx = box.v[1] - box.v[0] + 1, ny = box.v[3] - box.v[2] + 1, nz = box.v[5] - box.v[4] + 1;
+   if( beta == 0 || nx <= 0 || ny <= 0 || nz <= 0 ) return 0;
+   ProfScope prof( "addsgd", st );
    dim3 bs( 32, 4, 2 );
-   dim3 gs( ( b.ni - 2 * w + bs.x - 1 ) / bs.x, ( b.nj - 2 * w + bs.y - 1 ) / bs.y, ( b.nk - 2 * w + bs.z - 1 ) / bs.z );
-   k_addsgd<<<gs, bs, 0, st>>>( order, b, up, u, um, rho, dcx, dcy, dcz, strx, stry, strz, cox, coy, coz, beta );
+   dim3 gs( ( nx + bs.x - 1 ) / bs.x, ( ny + bs.y - 1 ) / bs.y, ( nz + bs.z - 1 ) / bs.z );
+   k_addsgd<<<gs, bs, 0, st>>>( order, b, box, up, u, um, rho, dcx, dcy, dcz, strx, stry, strz, cox, coy, coz, beta );
    count_launch();
    return check_launch( "k_addsgd" );
 }
@@ -638,6 +690,7 @@ int launch_bcfortsg( const Block& b, const Int36& wind, int nx, int ny, int nz, 
 		     const Int6& bccnd, const double* mu, const double* la, const Ptr6& bforce,
 		     const double* strx, const double* stry, cudaStream_t st )
 {
+   ProfScope prof( "bc", st );
    for( int s = 0; s < 6; s++ )
    {
       const int* w = wind.v + 6 * s;
@@ -671,10 +724,12 @@ int launch_bcfortsg( const Block& b, const Int36& wind, int nx, int ny, int nz, 
 }
 
 int launch_add_point_forces( int corder, long long npts, double* up, const double* rho, int n,
-			     const long long* pidx_, const double* f, double factor, cudaStream_t st )
+			     const long long* pidx_, const double* f, double factor, cudaStream_t st, double* up2,
+			     double factor2, long long nij, int kplane_lo, int kplane_hi )
 {
    if( n <= 0 ) return 0;
-   k_add_point_forces<<<( n + 127 ) / 128, 128, 0, st>>>( corder ? npts : 1, corder ? 1 : 3, up, rho, n, pidx_, f, factor );
+   k_add_point_forces<<<( n + 127 ) / 128, 128, 0, st>>>( corder ? npts : 1, corder ? 1 : 3, up, rho, n, pidx_, f, factor,
+							   up2, factor2, nij, kplane_lo, kplane_hi );
    count_launch();
    return check_launch( "k_add_point_forces" );
 }
@@ -685,6 +740,12 @@ int launch_gather_points( int corder, long long npts, const double* u, int n, co
    k_gather_points<<<( n + 127 ) / 128, 128, 0, st>>>( corder ? npts : 1, corder ? 1 : 3, u, n, pidx_, out );
    count_launch();
    return check_launch( "k_gather_points" );
+}
+int launch_fill_profile( const Block& b, double* a, const double* prof, cudaStream_t st )
+{
+   k_fill_profile<<<nblocks( b.npts, 256 ), 256, 0, st>>>( b, a, prof );
+   count_launch();
+   return check_launch( "k_fill_profile" );
 }
 int launch_halo_copy( const Block& b, double* field, int kplane, double* buf, int pack, cudaStream_t st )
 {

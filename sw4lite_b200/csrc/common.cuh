@@ -1,6 +1,8 @@
 // Shared declarations of the sw4b200 CUDA library (sm_100a only).
 #pragma once
+#ifndef SW4B200_EMULATE
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <stddef.h>
 
@@ -52,7 +54,18 @@ void count_launch( int n = 1 );
 cudaStream_t as_stream( void* s );
 
 // ---- launch wrappers implemented in the .cu files -------------------------------------------
-enum RhsMode { MODE_LU = 0, MODE_PRED = 1, MODE_CORR = 2 };
+// MODE_CORR forms uacc=(up-2u+um)/dt^2 on the fly and writes out-of-place; MODE_CORR_ACC reads a stored
+// uacc array (in `u`) and corrects `up` in place; MODE_SHELL_DPDMT: uacc on the 2-point shell only.
+enum RhsMode { MODE_LU = 0, MODE_PRED = 1, MODE_CORR = 2, MODE_CORR_ACC = 3, MODE_SHELL_DPDMT = 4 };
+
+// optional per-kernel device timing (sw4b200_profile_*): records an event pair around a launch
+struct ProfScope
+{
+   ProfScope( const char* name, cudaStream_t st );
+   ~ProfScope();
+   int slot;
+   cudaStream_t st;
+};
 
 struct RhsArgs
 {
@@ -60,6 +73,7 @@ struct RhsArgs
    int nk;	    // global interior size in k
    int onesided4, onesided5;
    double* out;	    // lu (MODE_LU) or up_out (PRED/CORR)
+   double* out2;    // PRED: uacc = (L(u)/h^2+fo)/rho (optional); SHELL_DPDMT: uacc
    const double *u, *um, *up; // PRED: u,um ; CORR: up,u,um (uacc formed on the fly); LU: u
    const double *mu, *la, *rho, *fo;
    const double *strx, *stry, *strz;
@@ -71,7 +85,7 @@ struct RhsArgs
 };
 
 int launch_rhs_v1( RhsMode mode, const RhsArgs& a, cudaStream_t st );
-int launch_rhs_fast( RhsMode mode, const RhsArgs& a, cudaStream_t st ); // optimized SoA path (rhs4sg_fast.cu)
+int launch_rhs_v1_rows( RhsMode mode, const RhsArgs& a, int k_lo, int k_hi, cudaStream_t st );
 int launch_shell_update( RhsMode mode, const RhsArgs& a, cudaStream_t st );
 
 int launch_predfort( const Block& b, double* up, const double* u, const double* um, const double* lu,
@@ -84,13 +98,19 @@ int launch_addsgd( int order, const Block& b, double* up, const double* u, const
 		   const double* dcx, const double* dcy, const double* dcz,
 		   const double* strx, const double* stry, const double* strz,
 		   const double* cox, const double* coy, const double* coz, double beta, cudaStream_t st );
+int launch_addsgd_box( int order, const Block& b, const Int6& box, double* up, const double* u, const double* um,
+		       const double* rho, const double* dcx, const double* dcy, const double* dcz, const double* strx,
+		       const double* stry, const double* strz, const double* cox, const double* coy,
+		       const double* coz, double beta, cudaStream_t st );
 int launch_bcfortsg( const Block& b, const Int36& wind, int nx, int ny, int nz, double* u, double h,
 		     const Int6& bccnd, const double* mu, const double* la, const Ptr6& bforce,
 		     const double* strx, const double* stry, cudaStream_t st );
 int launch_add_point_forces( int corder, long long npts, double* up, const double* rho, int n,
-			     const long long* pidx, const double* f, double factor, cudaStream_t st );
+			     const long long* pidx, const double* f, double factor, cudaStream_t st,
+			     double* up2 = 0, double factor2 = 0, long long nij = 0, int kplane_lo = 0, int kplane_hi = 0 );
 int launch_gather_points( int corder, long long npts, const double* u, int n, const long long* pidx,
 			  double* out, cudaStream_t st );
+int launch_fill_profile( const Block& b, double* a, const double* prof, cudaStream_t st );
 int launch_halo_copy( const Block& b, double* field, int kplane, double* buf, int pack, cudaStream_t st );
 
 // curvilinear (curvilinear.cu)

@@ -34,6 +34,9 @@ SIGNATURES = {
     "sw4b200_sync_stream": (I, [I]),
     "sw4b200_sync_device": (I, []),
     "sw4b200_kernel_launch_count": (I, []),
+    "sw4b200_profile_enable": (I, [I]),
+    "sw4b200_profile_reset": (I, []),
+    "sw4b200_profile_read": (I, [C.c_char_p, c_dp, c_llp]),
     "sw4b200_malloc": (VP, [C.c_size_t]),
     "sw4b200_free": (I, [VP]),
     "sw4b200_malloc_host": (VP, [C.c_size_t]),
@@ -73,6 +76,13 @@ SIGNATURES = {
     "sw4b200_grid_cycle": (I, [VP]),
     "sw4b200_grid_record": (I, [VP, c_dp]),
     "sw4b200_grid_step": (I, [VP, c_dp, c_dp, c_dp]),
+    "sw4b200_grid_predictor_part": (I, [VP, I, c_dp]),
+    "sw4b200_grid_corrector_part": (I, [VP, I, c_dp]),
+    "sw4b200_grid_set_source_series": (I, [VP, I, c_dp, c_dp]),
+    "sw4b200_grid_run": (I, [VP, I, I]),
+    "sw4b200_grid_fetch_records": (I, [VP, I, I, c_dp]),
+    "sw4b200_grid_fill_profile": (I, [VP, C.c_char_p, c_dp]),
+    "sw4b200_grid_set_stream": (I, [VP, I]),
     "sw4b200_grid_pack_halo": (I, [VP, I, VP, VP]),
     "sw4b200_grid_unpack_halo": (I, [VP, I, VP, VP]),
     "sw4b200_grid_sync": (I, [VP]),

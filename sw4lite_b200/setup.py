@@ -4,7 +4,7 @@ loop, restated for Cartesian single-grid problems.  Host-side numpy only; nothin
 hot path.  Parity of these arrays with the reference is checked in tests/test_setup.py."""
 import numpy as np
 
-from .solver import bStressFree, bSuperGrid, boundary_windows
+from .solver import bStressFree, bSuperGrid, bProcessor, boundary_windows
 
 
 def _psi0(xi):
@@ -72,10 +72,8 @@ class CartesianProblem:
             vpk[m], vsk[m], rhk[m] = lvp, lvs, lrho
         muk = rhk * vsk ** 2
         lak = rhk * vpk ** 2 - 2 * muk
-        plane = np.ones(self.ni * self.nj)
-        self.mu = np.repeat(muk, self.ni * self.nj) * np.tile(plane, self.nk)
-        self.la = np.repeat(lak, self.ni * self.nj) * np.tile(plane, self.nk)
-        self.rho = np.repeat(rhk, self.ni * self.nj) * np.tile(plane, self.nk)
+        # the medium is layered: keep the per-plane profiles, materialise 3-D fields only on demand
+        self.muk, self.lak, self.rhk = muk, lak, rhk
         # supergrid 1-D arrays (EW::assign_supergrid_damping_arrays, EW.C:4671-4801)
         width = gp * self.h
         xs = (np.arange(-1, nx + 3) - 1) * self.h
@@ -86,6 +84,18 @@ class CartesianProblem:
         # time step (EW::computeDT, EW.C:5041-5066): dt = cfl*h/sqrt(max (4mu+la)/rho)
         self.dt = cfl * self.h / np.sqrt(np.max((4 * muk + lak) / rhk))
         self.sources = []  # (i,j,k, fx,fy,fz, freq, t0)
+
+    @property
+    def mu(self):
+        return np.repeat(self.muk, self.ni * self.nj)
+
+    @property
+    def la(self):
+        return np.repeat(self.lak, self.ni * self.nj)
+
+    @property
+    def rho(self):
+        return np.repeat(self.rhk, self.ni * self.nj)
 
     def add_point_force(self, i, j, k, f, freq, t0=0.0):
         self.sources.append((int(i), int(j), int(k), float(f[0]), float(f[1]), float(f[2]), float(freq), float(t0)))
@@ -100,13 +110,35 @@ class CartesianProblem:
             out[n] = np.array(s[3:6]) * g
         return out
 
-    def make_block(self, device=0):
+    def slab(self, rank, nranks):
+        """z-slab `rank` of `nranks`: interior planes split evenly (the reference's decomp1d rule,
+        EW.C:2931-2985, applied to k), 2 halo planes towards each neighbour.  Returns
+        (bounds, onesided, bctype, halo_lo, halo_hi)."""
+        from .slabs import slab_range
+        k0, k1 = slab_range(self.nz, rank, nranks)
+        bounds = list(self.bounds); bounds[4], bounds[5] = k0 - 2, k1 + 2
+        onesided = list(self.onesided); bctype = list(self.bctype)
+        halo_lo, halo_hi = rank > 0, rank < nranks - 1
+        if halo_lo:
+            onesided[4] = 0; bctype[4] = bProcessor
+        if halo_hi:
+            onesided[5] = 0; bctype[5] = bProcessor
+        return tuple(bounds), onesided, bctype, halo_lo, halo_hi
+
+    def make_block(self, device=0, rank=0, nranks=1):
         from .solver import GridBlock
-        g = GridBlock(self.corder, self.bounds, (self.nx, self.ny, self.nz), self.h, self.dt, self.onesided,
-                      self.bctype, self.wind, sg_order=4, beta=self.beta, device=device)
-        for name in ("mu", "rho", "strx", "stry", "strz", "dcx", "dcy", "dcz", "cox", "coy", "coz"):
+        bounds, onesided, bctype, halo_lo, halo_hi = self.slab(rank, nranks)
+        g = GridBlock(self.corder, bounds, (self.nx, self.ny, self.nz), self.h, self.dt, onesided,
+                      bctype, boundary_windows(bounds, bctype), sg_order=4, beta=self.beta, device=device,
+                      halo_lo=halo_lo, halo_hi=halo_hi)
+        k0 = bounds[4] - self.bounds[4]
+        ks = slice(k0, k0 + g.nk)
+        for name in ("strx", "stry", "dcx", "dcy", "cox", "coy"):
             g.upload(name, getattr(self, name))
-        g.upload("lambda", self.la)
-        if self.sources:
-            g.set_source_points(self.source_points())
+        for name in ("strz", "dcz", "coz"):
+            g.upload(name, getattr(self, name)[ks])
+        g.fill_profile("mu", self.muk[ks]); g.fill_profile("lambda", self.lak[ks]); g.fill_profile("rho", self.rhk[ks])
+        g.src_sel = [n for n, s in enumerate(self.sources) if bounds[4] + 2 <= s[2] <= bounds[5] - 2]
+        if g.src_sel:
+            g.set_source_points(self.source_points()[g.src_sel])
         return g

@@ -1,0 +1,91 @@
+"""z-slab decomposition of one Cartesian grid over the GPUs of one node and the halo exchange that
+replaces the reference's MPI x-y halo swap (EW::communicate_array, EW.C:3247-3317;
+communicate_arrayCU_X/Y, EW_cuda.C:1699-1997) on this path: one process per GPU, 2 planes of the new
+solution per face, moved after the predictor and after the corrector (EW.C:2616, 2743).
+
+With the (i,j,k,c) layout a k-plane of one component is one contiguous run of ni*nj doubles, so a halo
+is 3 contiguous runs per face.  Two transports:
+  * "nccl": torch.distributed batched isend/irecv on packed halo buffers (also what the CPU `gloo`
+    tests drive through a numpy stand-in for the block),
+  * "p2p":  CUDA IPC peer mappings -- every rank copies its face planes straight into the neighbour's
+    halo planes over NVLink (cudaMemcpyAsync on peer pointers, no staging, no NCCL on the data path),
+    ordered by CUDA IPC events.
+The exchange of the face planes overlaps the computation of the slab's remaining rows: the face rows
+are computed first (sw4b200_grid_*_part(1)), their transfer is launched on a second stream, then the
+bulk (part 2) runs; the boundary conditions wait for both.
+"""
+import numpy as np
+
+
+def decomp1d(nglobal, myid, nproc, olap=4):
+    """EW::decomp1d (EW.C:2963-2985): block [s,e] of 1..nglobal for rank myid, blocks overlap by olap"""
+    nlocal = (nglobal + (nproc - 1) * olap) // nproc
+    deficit = (nglobal + (nproc - 1) * olap) % nproc
+    if myid < deficit:
+        s = myid * (nlocal - olap) + myid + 1
+        nlocal += 1
+    else:
+        s = myid * (nlocal - olap) + deficit + 1
+    return s, s + nlocal - 1
+
+
+def slab_range(nz, rank, nranks):
+    """interior planes [k0,k1] OWNED by slab `rank`: the decomp1d block minus the 2 padding planes
+    towards each neighbour"""
+    s, e = decomp1d(nz, rank, nranks)
+    return s + (2 if rank > 0 else 0), e - (2 if rank < nranks - 1 else 0)
+
+
+class HaloExchange:
+    """moves the face planes of Up between neighbouring slabs.  `blk` needs: ni, nj, pack(side) ->
+    tensor(3*2*ni*nj), unpack(side, tensor); torch.distributed must be initialised when nranks > 1."""
+
+    def __init__(self, blk, rank, nranks, device=None):
+        import torch
+        self.torch = torch
+        self.blk, self.rank, self.nranks = blk, rank, nranks
+        n = 6 * blk.ni * blk.nj
+        kw = dict(dtype=torch.float64, device=device if device is not None else "cpu")
+        self.send = [torch.zeros(n, **kw), torch.zeros(n, **kw)]
+        self.recv = [torch.zeros(n, **kw), torch.zeros(n, **kw)]
+        self.lo = rank - 1 if rank > 0 else None
+        self.hi = rank + 1 if rank < nranks - 1 else None
+        self.bytes_per_exchange = 8 * n * ((self.lo is not None) + (self.hi is not None))
+
+    def exchange(self):
+        import torch.distributed as dist
+        ops = []
+        for side, peer in ((0, self.lo), (1, self.hi)):
+            if peer is None:
+                continue
+            self.blk.pack(side, self.send[side])
+            ops.append(dist.P2POp(dist.isend, self.send[side], peer))
+            ops.append(dist.P2POp(dist.irecv, self.recv[side], peer))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for side, peer in ((0, self.lo), (1, self.hi)):
+            if peer is not None:
+                self.blk.unpack(side, self.recv[side])
+
+
+class SlabStepper:
+    """one time step of a z-slab (EW.C:2527-2842 with the halo swap on k): face rows -> exchange
+    (overlapped with the bulk rows) -> boundary conditions, twice per step."""
+
+    def __init__(self, blk, exchange):
+        self.blk, self.ex = blk, exchange
+
+    def step(self, f=None, ftt=None):
+        b = self.blk
+        b.predictor_part(1, f)
+        b.begin_exchange(self.ex)
+        b.predictor_part(2, f)
+        b.end_exchange(self.ex)
+        b.enforce_bc()
+        b.corrector_part(1, ftt)
+        b.begin_exchange(self.ex)
+        b.corrector_part(2, ftt)
+        b.end_exchange(self.ex)
+        b.enforce_bc()
+        b.cycle()

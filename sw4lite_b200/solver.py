@@ -119,6 +119,90 @@ class GridBlock:
     def cycle(self):
         L.check(self.lib.sw4b200_grid_cycle(self.h))
 
+    def predictor_part(self, part, f=None):
+        f = np.ascontiguousarray(f, dtype=np.float64) if (f is not None and self.nsrc) else None
+        L.check(self.lib.sw4b200_grid_predictor_part(self.h, int(part), _d(f)))
+
+    def corrector_part(self, part, ftt=None):
+        ftt = np.ascontiguousarray(ftt, dtype=np.float64) if (ftt is not None and self.nsrc) else None
+        L.check(self.lib.sw4b200_grid_corrector_part(self.h, int(part), _d(ftt)))
+
+    def fill_profile(self, name, kvalues):
+        a = np.ascontiguousarray(kvalues, dtype=np.float64)
+        if a.size != self.nk:
+            raise ValueError("profile of '%s' has %d values, the block has %d planes" % (name, a.size, self.nk))
+        L.check(self.lib.sw4b200_grid_fill_profile(self.h, name.encode(), _d(a)))
+
+    def set_source_series(self, f_all, ftt_all):
+        """f_all, ftt_all: (nsteps, nsrc, 3) source amplitudes of every step, kept on the device"""
+        f = np.ascontiguousarray(f_all, dtype=np.float64); ftt = np.ascontiguousarray(ftt_all, dtype=np.float64)
+        nsteps = f.shape[0] if self.nsrc else 0
+        L.check(self.lib.sw4b200_grid_set_source_series(self.h, nsteps, _d(f), _d(ftt)))
+
+    def run(self, first_step, nsteps):
+        """nsteps whole time steps with no host synchronisation (sources/receivers device resident)"""
+        L.check(self.lib.sw4b200_grid_run(self.h, int(first_step), int(nsteps)))
+
+    def fetch_records(self, first_step, nsteps):
+        out = np.zeros((nsteps, max(self.nrec, 1), 3))
+        if self.nrec:
+            L.check(self.lib.sw4b200_grid_fetch_records(self.h, int(first_step), int(nsteps), _d(out)))
+        return out[:, :self.nrec]
+
+    def set_stream(self, st):
+        L.check(self.lib.sw4b200_grid_set_stream(self.h, int(st)))
+
+    # ---- z-slab halo planes (see slabs.py).  torch is used for device buffers/streams only.
+    def pack(self, side, tensor, stream=None):
+        """the two interior planes next to face `side` (0 low-k, 1 high-k) of Up -> tensor(3*2*ni*nj)"""
+        L.check(self.lib.sw4b200_grid_pack_halo(self.h, int(side), C.c_void_p(tensor.data_ptr()), stream))
+
+    def unpack(self, side, tensor, stream=None):
+        L.check(self.lib.sw4b200_grid_unpack_halo(self.h, int(side), C.c_void_p(tensor.data_ptr()), stream))
+
+    def _streams(self):
+        import torch
+        if not hasattr(self, "_main"):
+            self._main = torch.cuda.ExternalStream(self.lib.sw4b200_stream(0))
+            self._comm = torch.cuda.ExternalStream(self.lib.sw4b200_stream(1))
+            self._ev_face = torch.cuda.Event()
+            self._ev_halo = torch.cuda.Event()
+        return self._main, self._comm
+
+    def begin_exchange(self, ex):
+        """start moving the face planes of Up on the communication stream; the caller goes on
+        launching the bulk rows on the compute stream"""
+        import torch
+        import torch.distributed as dist
+        main, comm = self._streams()
+        self._ev_face.record(main)
+        comm.wait_event(self._ev_face)
+        cs = C.c_void_p(comm.cuda_stream)
+        self._works = []
+        with torch.cuda.stream(comm):
+            ops = []
+            for side, peer in ((0, ex.lo), (1, ex.hi)):
+                if peer is None:
+                    continue
+                self.pack(side, ex.send[side], cs)
+                ops.append(dist.P2POp(dist.isend, ex.send[side], peer))
+                ops.append(dist.P2POp(dist.irecv, ex.recv[side], peer))
+            if ops:
+                self._works = dist.batch_isend_irecv(ops)
+
+    def end_exchange(self, ex):
+        import torch
+        main, comm = self._streams()
+        cs = C.c_void_p(comm.cuda_stream)
+        with torch.cuda.stream(comm):
+            for w in self._works:
+                w.wait()
+            for side, peer in ((0, ex.lo), (1, ex.hi)):
+                if peer is not None:
+                    self.unpack(side, ex.recv[side], cs)
+        self._ev_halo.record(comm)
+        main.wait_event(self._ev_halo)
+
     def record(self):
         out = np.zeros(3 * max(self.nrec, 1))
         if self.nrec:

@@ -1,0 +1,40 @@
+// TEST INFRASTRUCTURE ONLY: runs sw4lite_b200/csrc/rhs4sg_fast.cu's kernel on the CPU through
+// tests/emu/cuda_emu.h.  extern "C" entry for ctypes (tests/test_emu_fast.py).
+#include "cuda_emu.h"
+namespace emu {
+thread_local dim3 t_threadIdx;
+dim3 g_blockIdx, g_blockDim, g_gridDim;
+double* g_smem = 0;
+std::barrier<>* g_barrier = 0;
+}
+#include "../../sw4lite_b200/csrc/rhs4sg_fast.cu"
+
+using namespace sw4b200;
+
+extern "C" int emu_rhs_fast( int epi, int ifirst, int ilast, int jfirst, int jlast, int kfirst, int klast, int klo, int khi,
+			     int kchunk, const double* u, const double* mu, const double* la, const double* strx,
+			     const double* stry, const double* strz, double cof, double* out, double* out2,
+			     const double* um, const double* rho, const double* fo, double fac )
+{
+   FastArgs a;
+   a.b = make_block( 1, ifirst, ilast, jfirst, jlast, kfirst, klast );
+   a.klo = klo; a.khi = khi; a.kchunk = kchunk;
+   const long long n = a.b.npts;
+   for( int c = 0; c < 3; c++ )
+   {
+      a.u[c] = u + c * n;
+      a.out[c] = out + c * n;
+      a.out2[c] = out2 ? out2 + c * n : 0;
+      a.um[c] = um ? um + c * n : 0;
+      a.fo[c] = fo ? fo + c * n : 0;
+   }
+   a.mu = mu; a.la = la; a.strx = strx; a.stry = stry; a.strz = strz; a.cof = cof; a.rho = rho; a.fac = fac;
+   constexpr int TY = 8;
+   typedef fast::Cfg<TY> C;
+   dim3 bs( C::TX, TY, 1 );
+   dim3 gs( ( a.b.ni - 4 + C::TX - 1 ) / C::TX, ( a.b.nj - 4 + TY - 1 ) / TY, ( khi - klo + 1 + kchunk - 1 ) / kchunk );
+   if( epi == EPI_LU ) emu::launch( gs, bs, C::SMEM_DOUBLES, [&]() { k_rhs_fast<TY, EPI_LU>( a ); } );
+   else if( epi == EPI_PRED ) emu::launch( gs, bs, C::SMEM_DOUBLES, [&]() { k_rhs_fast<TY, EPI_PRED>( a ); } );
+   else emu::launch( gs, bs, C::SMEM_DOUBLES, [&]() { k_rhs_fast<TY, EPI_CORR>( a ); } );
+   return 0;
+}

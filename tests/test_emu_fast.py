@@ -1,0 +1,99 @@
+"""CPU test of the fast interior kernel's algebra and index logic: the CUDA source of
+sw4lite_b200/csrc/rhs4sg_fast.cu compiled by g++ through tests/emu/cuda_emu.h (one OS thread per
+CUDA thread) against the oracle.  This is test infrastructure for the kernel source, not a product
+path: the library itself has no CPU implementation."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+import pytest
+
+from tests.fields import Box, random_fields, relerr
+from tests.cpu_step import oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, "emu")
+LIB = os.path.join(EMU, "libemu_fast.so")
+SRC = [os.path.join(EMU, "emu_fast.cpp"), os.path.join(EMU, "cuda_emu.h"),
+       os.path.join(HERE, "..", "sw4lite_b200", "csrc", "rhs4sg_fast.cu"),
+       os.path.join(HERE, "..", "sw4lite_b200", "csrc", "common.cuh")]
+_dp = C.POINTER(C.c_double)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in SRC):
+        subprocess.check_call(["/usr/bin/g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-DSW4B200_EMULATE",
+                               "-ffp-contract=off", "-o", LIB, SRC[0]])
+    lib = C.CDLL(LIB)
+    lib.emu_rhs_fast.argtypes = [C.c_int] * 10 + [_dp] * 6 + [C.c_double] + [_dp] * 5 + [C.c_double]
+    return lib
+
+
+def d(a):
+    return a.ctypes.data_as(_dp) if a is not None else None
+
+
+def run(emu, epi, box, klo, khi, kchunk, f, cof, out, out2=None, um=None, rho=None, fo=None, fac=0.0):
+    emu.emu_rhs_fast(epi, *box.bounds, klo, khi, kchunk, d(f["u"]), d(f["mu"]), d(f["la"]), d(f["strx"]), d(f["stry"]),
+                     d(f["strz"]), cof, d(out), d(out2), d(um), d(rho), d(fo), fac)
+
+
+def cpu_lu(box, f, h, onesided=(0,) * 6, nk=None):
+    O = oracle()
+    acof, ghcof, bope, _ = O.get_stencil_coefficients()
+    lu = np.zeros(3 * box.npts)
+    O.rhs4sg(1, box.bounds, nk if nk is not None else box.nk - 4, onesided, acof, bope, ghcof, lu, f["u"], f["mu"],
+             f["la"], h, f["strx"], f["stry"], f["strz"])
+    return lu
+
+
+@pytest.mark.parametrize("dims,kchunk", [((45, 22, 20), 16), ((37, 13, 23), 7), ((70, 9, 9), 5)])
+def test_emu_lu_matches_oracle(emu, dims, kchunk):
+    box = Box(*dims)
+    f = random_fields(box, seed=21)
+    h = 0.7
+    ref = cpu_lu(box, f, h)
+    out = np.full(3 * box.npts, 55.0)
+    run(emu, 0, box, box.kfirst + 2, box.klast - 2, kchunk, f, 1 / h ** 2, out)
+    a = out.reshape(3, box.nk, box.nj, box.ni); b = ref.reshape(3, box.nk, box.nj, box.ni)
+    assert relerr(a[:, 2:-2, 2:-2, 2:-2], b[:, 2:-2, 2:-2, 2:-2]) < 1e-13
+    shell = np.ones((box.nk, box.nj, box.ni), dtype=bool); shell[2:-2, 2:-2, 2:-2] = False
+    assert np.all(a[:, shell] == 55.0)          # nothing outside the interior is written
+
+
+def test_emu_row_range_between_closures(emu):
+    """rows 7..nk-6 only (the closure rows belong to another kernel)"""
+    box = Box(40, 20, 26)
+    nk = box.nk - 4
+    f = random_fields(box, seed=22)
+    ref = cpu_lu(box, f, 1.0, onesided=(0, 0, 0, 0, 1, 1)).reshape(3, box.nk, box.nj, box.ni)
+    out = np.zeros(3 * box.npts)
+    run(emu, 0, box, 7, nk - 6, 100, f, 1.0, out)
+    a = out.reshape(3, box.nk, box.nj, box.ni)
+    k0 = 7 - box.kfirst; k1 = nk - 6 - box.kfirst
+    assert relerr(a[:, k0:k1 + 1, 2:-2, 2:-2], ref[:, k0:k1 + 1, 2:-2, 2:-2]) < 1e-13
+    assert np.all(a[:, :k0] == 0) and np.all(a[:, k1 + 1:] == 0)
+
+
+def test_emu_predictor_and_corrector_epilogues(emu):
+    box = Box(41, 19, 15)
+    f = random_fields(box, seed=23)
+    h, dt = 0.4, 0.05
+    O = oracle()
+    lu = cpu_lu(box, f, h)
+    up = np.zeros(3 * box.npts)
+    O.predfort(1, box.bounds, up, f["u"], f["um"], lu, f["fo"], f["rho"], dt * dt)
+    out = np.zeros(3 * box.npts); out2 = np.zeros(3 * box.npts)
+    run(emu, 1, box, box.kfirst + 2, box.klast - 2, 6, f, 1 / h ** 2, out, out2=out2, um=f["um"], rho=f["rho"], fo=f["fo"], fac=dt * dt)
+    inner = (slice(None), slice(2, -2), slice(2, -2), slice(2, -2))
+    r4 = lambda x: x.reshape(3, box.nk, box.nj, box.ni)
+    assert relerr(r4(out)[inner], r4(up)[inner]) < 1e-13
+    acc = (r4(lu) + r4(f["fo"])) / f["rho"].reshape(box.nk, box.nj, box.ni)
+    assert relerr(r4(out2)[inner], acc[inner]) < 1e-13
+    # corrector: up + dt^4/(12 rho) (L(u) + fo), in place
+    ref = f["up"].copy()
+    O.corrfort(1, box.bounds, ref, lu, f["fo"], f["rho"], dt ** 4)
+    out = f["up"].copy()
+    run(emu, 2, box, box.kfirst + 2, box.klast - 2, 6, f, 1 / h ** 2, out, um=out, rho=f["rho"], fo=f["fo"], fac=dt ** 4 / 12)
+    assert relerr(r4(out)[inner], r4(ref)[inner]) < 1e-13
