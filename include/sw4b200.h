@@ -241,10 +241,13 @@ int sw4b200_grid_fetch_records( sw4b200_grid* g, int first_step, int nsteps, dou
 int sw4b200_grid_fill_profile( sw4b200_grid* g, const char* name, const double* h_kvalues /* nk */ );
 /* run this block's kernels on library stream st (0..3) */
 int sw4b200_grid_set_stream( sw4b200_grid* g, int st );
-/* z-slab halo planes of Up: copy the 2 interior planes next to the low (side=0) / high (side=1)
- * face into d_dst (3*2*ni*nj doubles, component-major), or from d_src into the 2 halo planes. */
-int sw4b200_grid_pack_halo( sw4b200_grid* g, int side, double* d_dst, void* stream );
-int sw4b200_grid_unpack_halo( sw4b200_grid* g, int side, const double* d_src, void* stream );
+/* z-slab halo planes: copy the 2 interior planes of Up next to the low (side=0) / high (side=1) face
+ * into d_dst (3*2*ni*nj doubles, component-major), or from d_src into the 2 halo planes.  with_acc=1
+ * (the exchange after the predictor) appends the same planes of the stored acceleration, so that a
+ * slab run stays bit-identical to the undivided run; sw4b200_grid_halo_doubles gives the buffer size. */
+int sw4b200_grid_pack_halo( sw4b200_grid* g, int side, int with_acc, double* d_dst, void* stream );
+int sw4b200_grid_unpack_halo( sw4b200_grid* g, int side, int with_acc, const double* d_src, void* stream );
+int sw4b200_grid_halo_doubles( sw4b200_grid* g, int with_acc );
 int sw4b200_grid_sync( sw4b200_grid* g );
 
 #ifdef __cplusplus

@@ -132,7 +132,7 @@ static void fast_args( const RhsArgs& a, FastArgs& f )
    f.b = a.b;
    for( int c = 0; c < 3; c++ ) f.u[c] = a.u + c * a.b.npts;
    f.mu = a.mu; f.la = a.la; f.strx = a.strx; f.stry = a.stry; f.strz = a.strz;
-   f.cof = 1.0 / ( a.h * a.h );
+   f.cof6 = 1.0 / ( 6 * a.h * a.h ); f.cof144 = 1.0 / ( 144 * a.h * a.h );
    f.rho = a.rho;
    for( int c = 0; c < 3; c++ )
    {
@@ -919,7 +919,9 @@ static int corrector_dev( sw4b200_grid* g, int part )
    if( part != 2 )
    {
       // acceleration on the 2-point shell (ghost points, halo planes) from the boundary-conditioned predictor
+      // (the interior of a halo plane holds the neighbour's stored acceleration, moved with the predictor's halo)
       a.out2 = g->Uacc; a.up = g->Up; a.u = g->U; a.um = g->Um;
+      a.halo_lo = g->d.halo_lo; a.halo_hi = g->d.halo_hi;
       if( launch_shell_update( MODE_SHELL_DPDMT, a, g->st ) ) return 1;
    }
    a.out = g->Up; a.up = g->Up; a.u = g->Uacc; a.um = 0; a.out2 = 0; a.fo = 0;
@@ -1141,16 +1143,26 @@ int sw4b200_profile_read( const char* kernel, double* ms_total, long long* launc
    return 0;
 }
 
-int sw4b200_grid_pack_halo( sw4b200_grid* g, int side, double* d_dst, void* stream )
+int sw4b200_grid_pack_halo( sw4b200_grid* g, int side, int with_acc, double* d_dst, void* stream )
 {
    // interior planes next to the face: local plane offsets 2,3 (low) or nk-4,nk-3 (high)
    const int kplane = side == 0 ? 2 : g->b.nk - 4;
-   return launch_halo_copy( g->b, g->Up, kplane, d_dst, 1, stream ? (cudaStream_t)stream : g->st );
+   cudaStream_t st = stream ? (cudaStream_t)stream : g->st;
+   if( launch_halo_copy( g->b, g->Up, kplane, d_dst, 1, st ) ) return 1;
+   if( with_acc && g->fast ) return launch_halo_copy( g->b, g->Uacc, kplane, d_dst + 6 * g->b.nij, 1, st );
+   return 0;
 }
-int sw4b200_grid_unpack_halo( sw4b200_grid* g, int side, const double* d_src, void* stream )
+int sw4b200_grid_unpack_halo( sw4b200_grid* g, int side, int with_acc, const double* d_src, void* stream )
 {
    const int kplane = side == 0 ? 0 : g->b.nk - 2;
-   return launch_halo_copy( g->b, g->Up, kplane, (double*)d_src, 0, stream ? (cudaStream_t)stream : g->st );
+   cudaStream_t st = stream ? (cudaStream_t)stream : g->st;
+   if( launch_halo_copy( g->b, g->Up, kplane, (double*)d_src, 0, st ) ) return 1;
+   if( with_acc && g->fast ) return launch_halo_copy( g->b, g->Uacc, kplane, (double*)d_src + 6 * g->b.nij, 0, st );
+   return 0;
+}
+int sw4b200_grid_halo_doubles( sw4b200_grid* g, int with_acc )
+{
+   return (int)( ( with_acc && g->fast ? 12 : 6 ) * g->b.nij );
 }
 int sw4b200_grid_sync( sw4b200_grid* g )
 {

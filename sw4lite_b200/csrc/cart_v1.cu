@@ -224,38 +224,9 @@ __device__ __forceinline__ double sgd_point( int order, const double* __restrict
 }
 
 template <int MODE>
-__global__ void __launch_bounds__( 256 ) k_rhs_v1( RhsArgs a, int k_lo, int k_hi )
+__device__ __forceinline__ void rhs_epilogue( const RhsArgs& a, long long p, int i, int j, int k, double cof, const double r[3] )
 {
    const Block& b = a.b;
-   const int i = b.ifirst + 2 + blockIdx.x * blockDim.x + threadIdx.x;
-   const int j = b.jfirst + 2 + blockIdx.y * blockDim.y + threadIdx.y;
-   const int k = k_lo + blockIdx.z * blockDim.z + threadIdx.z;
-   if( i > b.ilast - 2 || j > b.jlast - 2 || k > k_hi ) return;
-   Acc<MODE> U = { a.u, a.um, a.up, b.sc, b.sp, 1.0 / ( a.dt * a.dt ) };
-   double sx[5], sy[5], sz[5];
-#pragma unroll
-   for( int m = 0; m < 5; m++ )
-   {
-      sx[m] = a.strx[i - b.ifirst + m - 2];
-      sy[m] = a.stry[j - b.jfirst + m - 2];
-   }
-   const long long p = pidx( b, i, j, k );
-   double r[3];
-   const bool low = a.onesided4 && k <= 6;
-   const bool high = a.onesided5 && k >= a.nk - 5;
-   if( low || high )
-   {
-      const long long pcol = pidx( b, i, j, b.kfirst );
-      rhs_closure_point( U, a.mu, a.la, pcol, b.kfirst, a.nk, low ? 0 : 1, low ? k : a.nk - k + 1,
-			 (long long)b.ni, b.nij, sx, sy, r );
-   }
-   else
-   {
-#pragma unroll
-      for( int m = 0; m < 5; m++ ) sz[m] = a.strz[k - b.kfirst + m - 2];
-      rhs_interior_point( U, a.mu, a.la, p, (long long)b.ni, b.nij, sx, sy, sz, r );
-   }
-   const double cof = 1.0 / ( a.h * a.h );
    if( MODE == MODE_LU )
    {
 #pragma unroll
@@ -320,6 +291,102 @@ __global__ void __launch_bounds__( 256 ) k_rhs_v1( RhsArgs a, int k_lo, int k_hi
    }
 }
 
+template <int MODE>
+__global__ void __launch_bounds__( 256 ) k_rhs_v1( RhsArgs a, int k_lo, int k_hi )
+{
+   const Block& b = a.b;
+   const int i = b.ifirst + 2 + blockIdx.x * blockDim.x + threadIdx.x;
+   const int j = b.jfirst + 2 + blockIdx.y * blockDim.y + threadIdx.y;
+   const int k = k_lo + blockIdx.z * blockDim.z + threadIdx.z;
+   if( i > b.ilast - 2 || j > b.jlast - 2 || k > k_hi ) return;
+   Acc<MODE> U = { a.u, a.um, a.up, b.sc, b.sp, 1.0 / ( a.dt * a.dt ) };
+   double sx[5], sy[5], sz[5];
+#pragma unroll
+   for( int m = 0; m < 5; m++ )
+   {
+      sx[m] = a.strx[i - b.ifirst + m - 2];
+      sy[m] = a.stry[j - b.jfirst + m - 2];
+   }
+   const long long p = pidx( b, i, j, k );
+   double r[3];
+   const bool low = a.onesided4 && k <= 6;
+   const bool high = a.onesided5 && k >= a.nk - 5;
+   if( low || high )
+   {
+      const long long pcol = pidx( b, i, j, b.kfirst );
+      rhs_closure_point( U, a.mu, a.la, pcol, b.kfirst, a.nk, low ? 0 : 1, low ? k : a.nk - k + 1,
+			 (long long)b.ni, b.nij, sx, sy, r );
+   }
+   else
+   {
+#pragma unroll
+      for( int m = 0; m < 5; m++ ) sz[m] = a.strz[k - b.kfirst + m - 2];
+      rhs_interior_point( U, a.mu, a.la, p, (long long)b.ni, b.nij, sx, sy, sz, r );
+   }
+   rhs_epilogue<MODE>( a, p, i, j, k, 1.0 / ( a.h * a.h ), r );
+}
+
+// SBP closure rows with the 9 planes they read staged in shared memory: one thread per (i,j)
+// column of a 32x8 tile computes rows kb_lo..kb_hi of one side (side 0: k=kb, planes 0..8;
+// side 1: k=nk-kb+1, planes nk-7..nk+1).  Same arithmetic as k_rhs_v1 (rhs_closure_point); the
+// neighbours come from shared memory instead of L1/L2.
+constexpr int CL_TX = 32, CL_TY = 8, CL_PX = CL_TX + 4, CL_PY = CL_TY + 4, CL_PLANE = CL_PX * CL_PY, CL_NP = 9;
+
+template <int MODE>
+__global__ void __launch_bounds__( CL_TX* CL_TY ) k_closure_staged( RhsArgs a, int side, int kb_lo, int kb_hi )
+{
+   extern __shared__ double sm[]; // [5 fields][9 planes][CL_PLANE]
+   const Block& b = a.b;
+   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * CL_TX + tx;
+   const int li0 = 2 + blockIdx.x * CL_TX, lj0 = 2 + blockIdx.y * CL_TY;
+   const int kbase = side == 0 ? 0 : a.nk - 7; // global k of staged plane 0
+   const double dt2i = 1.0 / ( a.dt * a.dt );
+   for( int idx = tid; idx < CL_PLANE; idx += CL_TX * CL_TY )
+   {
+      const int sy_ = idx / CL_PX, sx_ = idx - sy_ * CL_PX;
+      const int li = li0 - 2 + sx_, lj = lj0 - 2 + sy_;
+      const bool inb = li < b.ni && lj < b.nj;
+#pragma unroll
+      for( int s = 0; s < CL_NP; s++ )
+      {
+	 const long long p = inb ? (long long)li + (long long)b.ni * lj + b.nij * ( kbase + s - b.kfirst ) : 0;
+#pragma unroll
+	 for( int c = 0; c < 3; c++ )
+	 {
+	    const long long q = c * b.sc + b.sp * p;
+	    double v = 0;
+	    if( inb ) v = MODE == MODE_CORR ? dt2i * ( a.up[q] - 2 * a.u[q] + a.um[q] ) : a.u[q];
+	    sm[( c * CL_NP + s ) * CL_PLANE + idx] = v;
+	 }
+	 sm[( 3 * CL_NP + s ) * CL_PLANE + idx] = inb ? a.mu[p] : 0.0;
+	 sm[( 4 * CL_NP + s ) * CL_PLANE + idx] = inb ? a.la[p] : 0.0;
+      }
+   }
+   __syncthreads();
+   const int li = li0 + tx, lj = lj0 + ty;
+   if( li > b.ni - 3 || lj > b.nj - 3 ) return;
+   Acc<MODE_LU> U = { sm, 0, 0, (long long)CL_NP * CL_PLANE, 1, 0.0 };
+   const double* smu = sm + 3 * CL_NP * CL_PLANE;
+   const double* sla = sm + 4 * CL_NP * CL_PLANE;
+   double sx[5], sy[5];
+#pragma unroll
+   for( int m = 0; m < 5; m++ )
+   {
+      sx[m] = a.strx[li + m - 2];
+      sy[m] = a.stry[lj + m - 2];
+   }
+   const long long pcol = ( ty + 2 ) * CL_PX + tx + 2;
+   const double cof = 1.0 / ( a.h * a.h );
+   for( int kb = kb_lo; kb <= kb_hi; kb++ )
+   {
+      const int k = side == 0 ? kb : a.nk - kb + 1;
+      double r[3];
+      rhs_closure_point( U, smu, sla, pcol, kbase, a.nk, side, kb, (long long)CL_PX, (long long)CL_PLANE, sx, sy, r );
+      const long long p = (long long)li + (long long)b.ni * lj + b.nij * ( k - b.kfirst );
+      rhs_epilogue<MODE>( a, p, li + b.ifirst, lj + b.jfirst, k, cof, r );
+   }
+}
+
 // the 2-point shell where L(u) is never written (stays 0 in the reference): pred/corr with lu=0.
 // Enumerates the shell as 6 slabs: k-low, k-high (full planes), j-low, j-high, i-low, i-high.
 template <int MODE>
@@ -371,6 +438,8 @@ __global__ void k_shell_update( RhsArgs a )
       const long long p = (long long)i + (long long)b.ni * j + b.nij * k;
       if( MODE == MODE_SHELL_DPDMT )
       {
+	 const bool inner = i >= 2 && i < b.ni - 2 && j >= 2 && j < b.nj - 2;
+	 if( inner && ( ( a.halo_lo && k < 2 ) || ( a.halo_hi && k >= b.nk - 2 ) ) ) continue;
 	 const double dt2i = 1.0 / ( a.dt * a.dt );
 #pragma unroll
 	 for( int c = 0; c < 3; c++ )
@@ -604,11 +673,10 @@ inline int nblocks( long long n, int bs, int cap = 148 * 16 )
 
 } // namespace
 
-// rows [k_lo,k_hi] of the block (interior and/or closure rows)
-int launch_rhs_v1_rows( RhsMode mode, const RhsArgs& a, int k_lo, int k_hi, cudaStream_t st )
+static int launch_rows_general( RhsMode mode, const RhsArgs& a, int k_lo, int k_hi, cudaStream_t st )
 {
    const Block& b = a.b;
-   if( k_hi < k_lo || b.ni < 5 || b.nj < 5 ) return 0;
+   if( k_hi < k_lo ) return 0;
    ProfScope prof( "rhs_v1", st );
    dim3 bs( 32, 4, 2 );
    dim3 gs( ( b.ni - 4 + bs.x - 1 ) / bs.x, ( b.nj - 4 + bs.y - 1 ) / bs.y, ( k_hi - k_lo + 1 + bs.z - 1 ) / bs.z );
@@ -618,6 +686,57 @@ int launch_rhs_v1_rows( RhsMode mode, const RhsArgs& a, int k_lo, int k_hi, cuda
    else k_rhs_v1<MODE_CORR_ACC><<<gs, bs, 0, st>>>( a, k_lo, k_hi );
    count_launch();
    return check_launch( "k_rhs_v1" );
+}
+
+template <int MODE>
+static int launch_closure_t( const RhsArgs& a, int side, int kb_lo, int kb_hi, cudaStream_t st )
+{
+   static bool configured = false;
+   const size_t smem = (size_t)5 * CL_NP * CL_PLANE * sizeof( double );
+   if( !configured )
+   {
+      cudaError_t e = cudaFuncSetAttribute( k_closure_staged<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem );
+      if( e != cudaSuccess ) return set_error( "k_closure_staged: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString( e ) );
+      configured = true;
+   }
+   const Block& b = a.b;
+   ProfScope prof( "closure", st );
+   dim3 bs( CL_TX, CL_TY, 1 );
+   dim3 gs( ( b.ni - 4 + CL_TX - 1 ) / CL_TX, ( b.nj - 4 + CL_TY - 1 ) / CL_TY, 1 );
+   k_closure_staged<MODE><<<gs, bs, smem, st>>>( a, side, kb_lo, kb_hi );
+   count_launch();
+   return check_launch( "k_closure_staged" );
+}
+
+static int launch_closure( RhsMode mode, const RhsArgs& a, int side, int kb_lo, int kb_hi, cudaStream_t st )
+{
+   if( mode == MODE_LU ) return launch_closure_t<MODE_LU>( a, side, kb_lo, kb_hi, st );
+   if( mode == MODE_PRED ) return launch_closure_t<MODE_PRED>( a, side, kb_lo, kb_hi, st );
+   if( mode == MODE_CORR ) return launch_closure_t<MODE_CORR>( a, side, kb_lo, kb_hi, st );
+   return launch_closure_t<MODE_CORR_ACC>( a, side, kb_lo, kb_hi, st );
+}
+
+// rows [k_lo,k_hi] of the block (interior and/or closure rows): the SBP closure rows of a side go to the
+// staged kernel when the 9 planes they read lie inside the block, everything else to the general kernel
+int launch_rhs_v1_rows( RhsMode mode, const RhsArgs& a, int k_lo, int k_hi, cudaStream_t st )
+{
+   const Block& b = a.b;
+   if( k_hi < k_lo || b.ni < 5 || b.nj < 5 ) return 0;
+   int lo = k_lo, hi = k_hi;
+   if( a.onesided4 && lo <= 6 && b.kfirst <= 0 && b.klast >= 8 && a.nk >= 12 )
+   {
+      const int c1 = hi < 6 ? hi : 6;
+      if( launch_closure( mode, a, 0, lo < 1 ? 1 : lo, c1, st ) ) return 1;
+      lo = c1 + 1;
+   }
+   if( a.onesided5 && hi >= a.nk - 5 && lo <= hi && b.klast >= a.nk + 1 && b.kfirst <= a.nk - 7 && a.nk >= 12 )
+   {
+      const int c0 = lo > a.nk - 5 ? lo : a.nk - 5;
+      // rows k=c0..hi  <->  kb = nk-k+1
+      if( launch_closure( mode, a, 1, a.nk - hi + 1, a.nk - c0 + 1, st ) ) return 1;
+      hi = c0 - 1;
+   }
+   return launch_rows_general( mode, a, lo, hi, st );
 }
 
 int launch_rhs_v1( RhsMode mode, const RhsArgs& a, cudaStream_t st )
@@ -678,6 +797,8 @@ int launch_addsgd_box( int order, const Block& b, const Int6& box, double* up, c
 {
    const int nx = box.v[1] - box.v[0] + 1, ny = box.v[3] - box.v[2] + 1, nz = box.v[5] - box.v[4] + 1;
    if( beta == 0 || nx <= 0 || ny <= 0 || nz <= 0 ) return 0;
+   if( order == 4 && b.sp == 1 )
+      return launch_addsgd4_fast( b, box, up, u, um, rho, dcx, dcy, dcz, strx, stry, strz, cox, coy, coz, beta, st );
    ProfScope prof( "addsgd", st );
    dim3 bs( 32, 4, 2 );
    dim3 gs( ( nx + bs.x - 1 ) / bs.x, ( ny + bs.y - 1 ) / bs.y, ( nz + bs.z - 1 ) / bs.z );

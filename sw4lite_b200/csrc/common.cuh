@@ -82,6 +82,7 @@ struct RhsArgs
    const double *dcx, *dcy, *dcz, *cox, *coy, *coz;
    double beta;
    int sg_order;
+   int halo_lo, halo_hi; // SHELL_DPDMT: the k ghost planes of that side are halos whose interior is not to be touched
 };
 
 int launch_rhs_v1( RhsMode mode, const RhsArgs& a, cudaStream_t st );
@@ -102,6 +103,10 @@ int launch_addsgd_box( int order, const Block& b, const Int6& box, double* up, c
 		       const double* rho, const double* dcx, const double* dcy, const double* dcz, const double* strx,
 		       const double* stry, const double* strz, const double* cox, const double* coy,
 		       const double* coz, double beta, cudaStream_t st );
+int launch_addsgd4_fast( const Block& b, const Int6& box, double* up, const double* u, const double* um,
+			 const double* rho, const double* dcx, const double* dcy, const double* dcz, const double* strx,
+			 const double* stry, const double* strz, const double* cox, const double* coy, const double* coz,
+			 double beta, cudaStream_t st );
 int launch_bcfortsg( const Block& b, const Int36& wind, int nx, int ny, int nz, double* u, double h,
 		     const Int6& bccnd, const double* mu, const double* la, const Ptr6& bforce,
 		     const double* strx, const double* stry, cudaStream_t st );

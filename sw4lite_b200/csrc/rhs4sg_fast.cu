@@ -33,7 +33,7 @@ struct FastArgs
    const double* u[3];	 // input field (u for LU/PRED, uacc for CORR), halo'd reads
    const double *mu, *la;
    const double *strx, *stry, *strz;
-   double cof;	     // 1/h^2
+   double cof6, cof144; // 1/(6 h^2), 1/(144 h^2)
    // epilogue
    double* out[3];	// LU: lu ; PRED: up ; CORR: up_out
    double* out2[3];	// PRED: uacc = (L(u)/h^2+fo)/rho (may be null)
@@ -367,33 +367,35 @@ __global__ void __launch_bounds__( 32 * TY, 1 ) k_rhs_fast( const FastArgs a )
 	 const double y1 = d0u( ey[-2 * TX], ey[-TX], ey[TX], ey[2 * TX] );
 	 const double y2 = d0u( ey[PY * TX - 2 * TX], ey[PY * TX - TX], ey[PY * TX + TX], ey[PY * TX + 2 * TX] );
 	 const double y3 = d0u( ey[2 * PY * TX - 2 * TX], ey[2 * PY * TX - TX], ey[2 * PY * TX + TX], ey[2 * PY * TX + 2 * TX] );
+	 // lu_c = cof * ( rz_c/6 + mixed_c/144 )
 	 double r[3];
-	 r[0] = ( 1.0 / 6 ) * rz[0] + ( 1.0 / 144 ) * ( sx * ( x1 + sy * y1 + szk * t1 ) );
-	 r[1] = ( 1.0 / 6 ) * rz[1] + ( 1.0 / 144 ) * ( sy * ( sx * x2 + y2 + szk * t2 ) );
-	 r[2] = ( 1.0 / 6 ) * rz[2] + ( 1.0 / 144 ) * ( szk * ( sx * x3 + sy * y3 + t3 ) );
+	 r[0] = a.cof6 * rz[0] + a.cof144 * ( sx * ( x1 + sy * y1 + szk * t1 ) );
+	 r[1] = a.cof6 * rz[1] + a.cof144 * ( sy * ( sx * x2 + y2 + szk * t2 ) );
+	 r[2] = a.cof6 * rz[2] + a.cof144 * ( szk * ( sx * x3 + sy * y3 + t3 ) );
 	 const long long q = b.nij * ( k - b.kfirst ) + gown;
 	 if( EPI == EPI_LU )
 	 {
 #pragma unroll
-	    for( int c = 0; c < 3; c++ ) a.out[c][q] = a.cof * r[c];
+	    for( int c = 0; c < 3; c++ ) a.out[c][q] = r[c];
 	 }
 	 else if( EPI == EPI_PRED )
 	 {
-	    const double f = a.fac / e_rho;
+	    const double rinv = 1.0 / e_rho; // one division per point; dt^2/rho and acc/rho are formed from it
+	    const double f = a.fac * rinv;
 	    const double uk[3] = { cu[2], cv[2], cw[2] };
 #pragma unroll
 	    for( int c = 0; c < 3; c++ )
 	    {
-	       const double acc = a.cof * r[c] + e_fo[c];
+	       const double acc = r[c] + e_fo[c];
 	       a.out[c][q] = 2 * uk[c] - e_um[c] + f * acc;
-	       if( a.out2[0] ) a.out2[c][q] = acc / e_rho;
+	       if( a.out2[0] ) a.out2[c][q] = acc * rinv;
 	    }
 	 }
 	 else
 	 {
 	    const double f = a.fac / e_rho;
 #pragma unroll
-	    for( int c = 0; c < 3; c++ ) a.out[c][q] = e_um[c] + f * ( a.cof * r[c] + e_fo[c] );
+	    for( int c = 0; c < 3; c++ ) a.out[c][q] = e_um[c] + f * ( r[c] + e_fo[c] );
 	 }
       }
       slot = nslot;

@@ -83,8 +83,9 @@ SIGNATURES = {
     "sw4b200_grid_fetch_records": (I, [VP, I, I, c_dp]),
     "sw4b200_grid_fill_profile": (I, [VP, C.c_char_p, c_dp]),
     "sw4b200_grid_set_stream": (I, [VP, I]),
-    "sw4b200_grid_pack_halo": (I, [VP, I, VP, VP]),
-    "sw4b200_grid_unpack_halo": (I, [VP, I, VP, VP]),
+    "sw4b200_grid_pack_halo": (I, [VP, I, I, VP, VP]),
+    "sw4b200_grid_unpack_halo": (I, [VP, I, I, VP, VP]),
+    "sw4b200_grid_halo_doubles": (I, [VP, I]),
     "sw4b200_grid_sync": (I, [VP]),
 }
 

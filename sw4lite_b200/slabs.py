@@ -44,29 +44,31 @@ class HaloExchange:
         import torch
         self.torch = torch
         self.blk, self.rank, self.nranks = blk, rank, nranks
-        n = 6 * blk.ni * blk.nj
+        n = 12 * blk.ni * blk.nj          # Up and (after the predictor) the stored acceleration
         kw = dict(dtype=torch.float64, device=device if device is not None else "cpu")
         self.send = [torch.zeros(n, **kw), torch.zeros(n, **kw)]
         self.recv = [torch.zeros(n, **kw), torch.zeros(n, **kw)]
         self.lo = rank - 1 if rank > 0 else None
         self.hi = rank + 1 if rank < nranks - 1 else None
-        self.bytes_per_exchange = 8 * n * ((self.lo is not None) + (self.hi is not None))
+        self.bytes_per_exchange = 8 * (n // 2) * ((self.lo is not None) + (self.hi is not None))   # Up only
 
-    def exchange(self):
+    def exchange(self, with_acc=False):
+        """blocking form (the overlapped form is GridBlock.begin_exchange / end_exchange)"""
         import torch.distributed as dist
+        n = self.blk.halo_doubles(with_acc)
         ops = []
         for side, peer in ((0, self.lo), (1, self.hi)):
             if peer is None:
                 continue
-            self.blk.pack(side, self.send[side])
-            ops.append(dist.P2POp(dist.isend, self.send[side], peer))
-            ops.append(dist.P2POp(dist.irecv, self.recv[side], peer))
+            self.blk.pack(side, self.send[side], with_acc=with_acc)
+            ops.append(dist.P2POp(dist.isend, self.send[side][:n], peer))
+            ops.append(dist.P2POp(dist.irecv, self.recv[side][:n], peer))
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
         for side, peer in ((0, self.lo), (1, self.hi)):
             if peer is not None:
-                self.blk.unpack(side, self.recv[side])
+                self.blk.unpack(side, self.recv[side], with_acc=with_acc)
 
 
 class SlabStepper:
@@ -79,9 +81,9 @@ class SlabStepper:
     def step(self, f=None, ftt=None):
         b = self.blk
         b.predictor_part(1, f)
-        b.begin_exchange(self.ex)
+        b.begin_exchange(self.ex, with_acc=True)    # Up and the stored acceleration of the face planes
         b.predictor_part(2, f)
-        b.end_exchange(self.ex)
+        b.end_exchange(self.ex, with_acc=True)
         b.enforce_bc()
         b.corrector_part(1, ftt)
         b.begin_exchange(self.ex)

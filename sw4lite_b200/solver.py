@@ -153,12 +153,16 @@ class GridBlock:
         L.check(self.lib.sw4b200_grid_set_stream(self.h, int(st)))
 
     # ---- z-slab halo planes (see slabs.py).  torch is used for device buffers/streams only.
-    def pack(self, side, tensor, stream=None):
-        """the two interior planes next to face `side` (0 low-k, 1 high-k) of Up -> tensor(3*2*ni*nj)"""
-        L.check(self.lib.sw4b200_grid_pack_halo(self.h, int(side), C.c_void_p(tensor.data_ptr()), stream))
+    def pack(self, side, tensor, stream=None, with_acc=False):
+        """the two interior planes next to face `side` (0 low-k, 1 high-k) of Up (+ the stored
+        acceleration if with_acc) -> tensor"""
+        L.check(self.lib.sw4b200_grid_pack_halo(self.h, int(side), int(with_acc), C.c_void_p(tensor.data_ptr()), stream))
 
-    def unpack(self, side, tensor, stream=None):
-        L.check(self.lib.sw4b200_grid_unpack_halo(self.h, int(side), C.c_void_p(tensor.data_ptr()), stream))
+    def unpack(self, side, tensor, stream=None, with_acc=False):
+        L.check(self.lib.sw4b200_grid_unpack_halo(self.h, int(side), int(with_acc), C.c_void_p(tensor.data_ptr()), stream))
+
+    def halo_doubles(self, with_acc):
+        return int(self.lib.sw4b200_grid_halo_doubles(self.h, int(with_acc)))
 
     def _streams(self):
         import torch
@@ -169,7 +173,7 @@ class GridBlock:
             self._ev_halo = torch.cuda.Event()
         return self._main, self._comm
 
-    def begin_exchange(self, ex):
+    def begin_exchange(self, ex, with_acc=False):
         """start moving the face planes of Up on the communication stream; the caller goes on
         launching the bulk rows on the compute stream"""
         import torch
@@ -178,19 +182,20 @@ class GridBlock:
         self._ev_face.record(main)
         comm.wait_event(self._ev_face)
         cs = C.c_void_p(comm.cuda_stream)
+        n = self.halo_doubles(with_acc)
         self._works = []
         with torch.cuda.stream(comm):
             ops = []
             for side, peer in ((0, ex.lo), (1, ex.hi)):
                 if peer is None:
                     continue
-                self.pack(side, ex.send[side], cs)
-                ops.append(dist.P2POp(dist.isend, ex.send[side], peer))
-                ops.append(dist.P2POp(dist.irecv, ex.recv[side], peer))
+                self.pack(side, ex.send[side], cs, with_acc)
+                ops.append(dist.P2POp(dist.isend, ex.send[side][:n], peer))
+                ops.append(dist.P2POp(dist.irecv, ex.recv[side][:n], peer))
             if ops:
                 self._works = dist.batch_isend_irecv(ops)
 
-    def end_exchange(self, ex):
+    def end_exchange(self, ex, with_acc=False):
         import torch
         main, comm = self._streams()
         cs = C.c_void_p(comm.cuda_stream)
@@ -199,7 +204,7 @@ class GridBlock:
                 w.wait()
             for side, peer in ((0, ex.lo), (1, ex.hi)):
                 if peer is not None:
-                    self.unpack(side, ex.recv[side], cs)
+                    self.unpack(side, ex.recv[side], cs, with_acc)
         self._ev_halo.record(comm)
         main.wait_event(self._ev_halo)
 

@@ -28,7 +28,7 @@ extern "C" int emu_rhs_fast( int epi, int ifirst, int ilast, int jfirst, int jla
       a.um[c] = um ? um + c * n : 0;
       a.fo[c] = fo ? fo + c * n : 0;
    }
-   a.mu = mu; a.la = la; a.strx = strx; a.stry = stry; a.strz = strz; a.cof = cof; a.rho = rho; a.fac = fac;
+   a.mu = mu; a.la = la; a.strx = strx; a.stry = stry; a.strz = strz; a.cof6 = cof / 6; a.cof144 = cof / 144; a.rho = rho; a.fac = fac;
    constexpr int TY = 8;
    typedef fast::Cfg<TY> C;
    dim3 bs( C::TX, TY, 1 );

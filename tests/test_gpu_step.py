@@ -73,3 +73,106 @@ def test_pointsource_per_step_parity_and_error_line(tmp_path):
     assert line == GOLDEN_LINE
     for a, b in zip((ew.t,) + tuple(errs), GOLDEN_FILE):
         assert abs(a - b) <= 1e-10 * abs(b)
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic blocks against the oracle's unfused kernel sequence (tests/cpu_step.py)
+def _problem(corder=1, nz=34):
+    from sw4lite_b200.setup import CartesianProblem
+    prob = CartesianProblem(37, 30, nz, h=100.0, gp=7, corder=corder, layers=[(1500.0, 6000.0, 3464.0, 2700.0)])
+    prob.add_point_force(18, 14, 8, (1e12, 2e12, -1e12), freq=2.0)
+    prob.add_point_force(20, 16, nz // 2 + 1, (-2e12, 1e12, 1e12), freq=3.0)
+    return prob
+
+
+def _initial(prob, seed=5):
+    r = np.random.default_rng(seed)
+    u0 = r.uniform(-1e-3, 1e-3, 3 * prob.npts)
+    return u0, u0 + r.uniform(-1e-5, 1e-5, 3 * prob.npts)
+
+
+@pytest.mark.parametrize("corder", [1, 0])
+def test_synthetic_block_steps_match_oracle(corder):
+    """free surface (SBP closure rows) + supergrid layers + layered medium + two point forces, 6 steps"""
+    from tests.cpu_step import OracleStepper
+    prob = _problem(corder)
+    blk = prob.make_block()
+    cpu = OracleStepper(prob)
+    u0, um0 = _initial(prob)
+    blk.upload("U", u0); blk.upload("Um", um0)
+    cpu.U[:] = u0; cpu.Um[:] = um0
+    t = 0.0
+    for step in range(6):
+        f, ftt = prob.forces(t), prob.forces(t, tt=True)
+        blk.step(f, ftt); cpu.step(f, ftt)
+        t += prob.dt
+        assert relerr(blk.download("U"), cpu.U) < 1e-12, "step %d" % (step + 1)
+
+
+def test_resident_run_equals_stepwise_and_records():
+    """sw4b200_grid_run (sources/receivers device resident, no host sync) == the per-step API, bit for bit"""
+    prob = _problem()
+    u0, um0 = _initial(prob)
+    rec = np.array([[5, 6, 1], [18, 14, 1], [30, 20, 3]], dtype=np.int32)
+    n = 5
+    f_all = np.array([prob.forces(s * prob.dt) for s in range(n)])
+    ftt_all = np.array([prob.forces(s * prob.dt, tt=True) for s in range(n)])
+    a = prob.make_block(); b = prob.make_block()
+    for blk in (a, b):
+        blk.upload("U", u0); blk.upload("Um", um0); blk.set_receiver_points(rec)
+    recs = np.array([a.step(f_all[s], ftt_all[s], record=True) for s in range(n)])
+    b.set_source_series(f_all, ftt_all)
+    b.run(0, 2); b.run(2, 3)
+    assert np.array_equal(a.download("U"), b.download("U")) and np.array_equal(a.download("Um"), b.download("Um"))
+    assert np.array_equal(recs, b.fetch_records(0, n))
+    assert np.abs(recs).max() > 0
+
+
+@pytest.mark.parametrize("nslabs", [2, 3])
+def test_slabs_on_one_gpu_reproduce_single_block(nslabs):
+    """z-slab blocks (face rows first, halo planes moved with pack/unpack, bulk rows after) driven from
+    one process on one GPU == the undivided block, bit for bit"""
+    import torch
+    prob = _problem(nz=41)
+    u0, um0 = _initial(prob)
+    whole = prob.make_block()
+    whole.upload("U", u0); whole.upload("Um", um0)
+    slabs = [prob.make_block(rank=r, nranks=nslabs) for r in range(nslabs)]
+    nij = whole.ni * whole.nj
+    full = lambda a: a.reshape(3, whole.nk, nij)
+    for s in slabs:
+        k0 = s.bounds[4] - whole.bounds[4]
+        s.upload("U", np.ascontiguousarray(full(u0)[:, k0:k0 + s.nk]).ravel())
+        s.upload("Um", np.ascontiguousarray(full(um0)[:, k0:k0 + s.nk]).ravel())
+    buf = [[torch.zeros(12 * nij, dtype=torch.float64, device="cuda") for _ in range(2)] for _ in slabs]
+
+    def exchange(with_acc=False):
+        for r, s in enumerate(slabs):
+            for side in (0, 1):
+                if (side == 0 and r > 0) or (side == 1 and r < nslabs - 1):
+                    s.pack(side, buf[r][side], with_acc=with_acc)
+        for r, s in enumerate(slabs):
+            if r > 0:
+                s.unpack(0, buf[r - 1][1], with_acc=with_acc)
+            if r < nslabs - 1:
+                s.unpack(1, buf[r + 1][0], with_acc=with_acc)
+
+    t = 0.0
+    for step in range(5):
+        f, ftt = prob.forces(t), prob.forces(t, tt=True)
+        whole.step(f, ftt)
+        for s in slabs:
+            s.predictor_part(1, f[s.src_sel])
+        exchange(with_acc=True)
+        for s in slabs:
+            s.predictor_part(2, f[s.src_sel]); s.enforce_bc(); s.corrector_part(1, ftt[s.src_sel])
+        exchange()
+        for s in slabs:
+            s.corrector_part(2, ftt[s.src_sel]); s.enforce_bc(); s.cycle()
+        t += prob.dt
+    ref = full(whole.download("U"))
+    assert np.abs(ref).max() > 0
+    for s in slabs:
+        k0 = s.bounds[4] - whole.bounds[4]
+        own = s.download("U").reshape(3, s.nk, nij)[:, 2:-2]
+        assert np.array_equal(own, ref[:, k0 + 2:k0 + s.nk - 2]), "slab at k0=%d" % s.bounds[4]

@@ -40,11 +40,16 @@ class CpuSlab:
         nij = self.ni * self.nj
         return self.st.Up.reshape(3, self.nk, nij)[:, k0:k0 + 2, :]
 
-    def pack(self, side, t):
-        t.copy_(torch.from_numpy(np.ascontiguousarray(self._planes(2 if side == 0 else self.nk - 4)).ravel()))
+    def halo_doubles(self, with_acc):
+        return 6 * self.ni * self.nj
 
-    def unpack(self, side, t):
-        self._planes(0 if side == 0 else self.nk - 2)[...] = t.numpy().reshape(3, 2, -1)
+    def pack(self, side, t, with_acc=False):
+        n = self.halo_doubles(False)
+        t[:n].copy_(torch.from_numpy(np.ascontiguousarray(self._planes(2 if side == 0 else self.nk - 4)).ravel()))
+
+    def unpack(self, side, t, with_acc=False):
+        n = self.halo_doubles(False)
+        self._planes(0 if side == 0 else self.nk - 2)[...] = t[:n].numpy().reshape(3, 2, -1)
 
     def predictor_part(self, part, f):
         if part == 1:
@@ -54,10 +59,10 @@ class CpuSlab:
         if part == 1:
             self.st.corrector(ftt)
 
-    def begin_exchange(self, ex):
-        ex.exchange()
+    def begin_exchange(self, ex, with_acc=False):
+        ex.exchange(with_acc)
 
-    def end_exchange(self, ex):
+    def end_exchange(self, ex, with_acc=False):
         pass
 
     def enforce_bc(self):
