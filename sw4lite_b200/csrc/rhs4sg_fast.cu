@@ -20,6 +20,7 @@
 // This file is also compiled by g++ as plain C++ (SW4B200_EMULATE) by tests/emu: the CPU test of
 // the kernel's index logic and algebra.  That build is test infrastructure, never a product path.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace sw4b200 {
 
@@ -439,9 +440,24 @@ int fast_kchunk( const Block& b, int nplanes, int ty )
    return (int)kc;
 }
 
+int launch_fast2( int epi, FastArgs a, cudaStream_t st );
+
+// SW4B200_FAST_GEN=1 selects the first-generation kernel (kept for A/B measurements)
+static int fast_generation()
+{
+   static int v = -1;
+   if( v < 0 )
+   {
+      const char* e = getenv( "SW4B200_FAST_GEN" );
+      v = ( e && e[0] == '1' ) ? 1 : 2;
+   }
+   return v;
+}
+
 int launch_fast( int epi, FastArgs a, cudaStream_t st )
 {
    if( a.khi < a.klo ) return 0;
+   if( fast_generation() == 2 ) return launch_fast2( epi, a, st );
    if( a.kchunk <= 0 ) a.kchunk = fast_kchunk( a.b, a.khi - a.klo + 1, 8 );
    switch( epi )
    {

@@ -8,10 +8,11 @@ double* g_smem = 0;
 std::barrier<>* g_barrier = 0;
 }
 #include "../../sw4lite_b200/csrc/rhs4sg_fast.cu"
+#include "../../sw4lite_b200/csrc/rhs4sg_fast2.cu"
 
 using namespace sw4b200;
 
-extern "C" int emu_rhs_fast( int epi, int ifirst, int ilast, int jfirst, int jlast, int kfirst, int klast, int klo, int khi,
+extern "C" int emu_rhs_fast( int gen, int epi, int ifirst, int ilast, int jfirst, int jlast, int kfirst, int klast, int klo, int khi,
 			     int kchunk, const double* u, const double* mu, const double* la, const double* strx,
 			     const double* stry, const double* strz, double cof, double* out, double* out2,
 			     const double* um, const double* rho, const double* fo, double fac )
@@ -33,6 +34,14 @@ extern "C" int emu_rhs_fast( int epi, int ifirst, int ilast, int jfirst, int jla
    typedef fast::Cfg<TY> C;
    dim3 bs( C::TX, TY, 1 );
    dim3 gs( ( a.b.ni - 4 + C::TX - 1 ) / C::TX, ( a.b.nj - 4 + TY - 1 ) / TY, ( khi - klo + 1 + kchunk - 1 ) / kchunk );
+   if( gen == 2 )
+   {
+      typedef fast2::Cfg<TY> C2;
+      if( epi == EPI_LU ) emu::launch( gs, bs, C2::SMEM_DOUBLES, [&]() { k_rhs_fast2<TY, EPI_LU>( a ); } );
+      else if( epi == EPI_PRED ) emu::launch( gs, bs, C2::SMEM_DOUBLES, [&]() { k_rhs_fast2<TY, EPI_PRED>( a ); } );
+      else emu::launch( gs, bs, C2::SMEM_DOUBLES, [&]() { k_rhs_fast2<TY, EPI_CORR>( a ); } );
+      return 0;
+   }
    if( epi == EPI_LU ) emu::launch( gs, bs, C::SMEM_DOUBLES, [&]() { k_rhs_fast<TY, EPI_LU>( a ); } );
    else if( epi == EPI_PRED ) emu::launch( gs, bs, C::SMEM_DOUBLES, [&]() { k_rhs_fast<TY, EPI_PRED>( a ); } );
    else emu::launch( gs, bs, C::SMEM_DOUBLES, [&]() { k_rhs_fast<TY, EPI_CORR>( a ); } );

@@ -16,8 +16,10 @@ EMU = os.path.join(HERE, "emu")
 LIB = os.path.join(EMU, "libemu_fast.so")
 SRC = [os.path.join(EMU, "emu_fast.cpp"), os.path.join(EMU, "cuda_emu.h"),
        os.path.join(HERE, "..", "sw4lite_b200", "csrc", "rhs4sg_fast.cu"),
+       os.path.join(HERE, "..", "sw4lite_b200", "csrc", "rhs4sg_fast2.cu"),
        os.path.join(HERE, "..", "sw4lite_b200", "csrc", "common.cuh")]
 _dp = C.POINTER(C.c_double)
+GEN = 2  # generation of the fast kernel under test (rhs4sg_fast2.cu is the product path)
 
 
 @pytest.fixture(scope="module")
@@ -26,7 +28,7 @@ def emu():
         subprocess.check_call(["/usr/bin/g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-DSW4B200_EMULATE",
                                "-ffp-contract=off", "-o", LIB, SRC[0]])
     lib = C.CDLL(LIB)
-    lib.emu_rhs_fast.argtypes = [C.c_int] * 10 + [_dp] * 6 + [C.c_double] + [_dp] * 5 + [C.c_double]
+    lib.emu_rhs_fast.argtypes = [C.c_int] * 11 + [_dp] * 6 + [C.c_double] + [_dp] * 5 + [C.c_double]
     return lib
 
 
@@ -35,7 +37,7 @@ def d(a):
 
 
 def run(emu, epi, box, klo, khi, kchunk, f, cof, out, out2=None, um=None, rho=None, fo=None, fac=0.0):
-    emu.emu_rhs_fast(epi, *box.bounds, klo, khi, kchunk, d(f["u"]), d(f["mu"]), d(f["la"]), d(f["strx"]), d(f["stry"]),
+    emu.emu_rhs_fast(GEN, epi, *box.bounds, klo, khi, kchunk, d(f["u"]), d(f["mu"]), d(f["la"]), d(f["strx"]), d(f["stry"]),
                      d(f["strz"]), cof, d(out), d(out2), d(um), d(rho), d(fo), fac)
 
 
