@@ -216,6 +216,9 @@ int sw4b200_grid_set_receiver_points( sw4b200_grid* g, int n, const int* h_ijk /
 
 /* step phases; h_f / h_ftt = 3*n source values at time t (F and its 2nd time derivative) or NULL */
 int sw4b200_grid_predictor( sw4b200_grid* g, const double* h_f );      /* EW.C:2537-2584           */
+/* EW::enforceCartTopo (EW.C:3504-3531) on the new solution (Up) of the top Cartesian block and of the
+ * curvilinear block above it; call after sw4b200_grid_enforce_bc of both, as EW::enforceBC does (EW.C:3500) */
+int sw4b200_grid_enforce_cart_topo( sw4b200_grid* gcart, sw4b200_grid* gcurv );
 int sw4b200_grid_enforce_bc( sw4b200_grid* g );                        /* EW.C:2622-2631 / 2748-2757 on Up, using the uploaded bforce arrays */
 int sw4b200_grid_corrector( sw4b200_grid* g, const double* h_ftt );    /* EW.C:2644-2717           */
 int sw4b200_grid_cycle( sw4b200_grid* g );                             /* EW.C:3060-3082           */

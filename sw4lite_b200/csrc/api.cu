@@ -238,6 +238,7 @@ struct sw4b200_grid
    cudaStream_t st;
    double *U, *Um, *Up, *Uacc; // Uacc: stored acceleration (SoA fast path) / second Up buffer (general path)
    double *mu, *la, *rho, *jac, *met;
+   double* Lu;		       // curvilinear blocks: L(u) scratch of the unfused sequence
    bool fast;		       // SoA Cartesian throughput path
    std::vector<double>* h_dc[3]; // host copies of the damping arrays -> boxes where the damping is non-zero
    std::vector<Int6>* sgd_boxes;
@@ -617,6 +618,8 @@ sw4b200_grid* sw4b200_grid_create( const sw4b200_grid_desc* desc )
    {
       if( !( g->jac = (double*)sw4b200_malloc( np * 8 ) ) ) return 0;
       if( !( g->met = (double*)sw4b200_malloc( 4 * np * 8 ) ) ) return 0;
+      if( !( g->Lu = (double*)sw4b200_malloc( 3 * np * 8 ) ) ) return 0;
+      cudaMemsetAsync( g->Lu, 0, 3 * np * 8, g->st );
    }
    const size_t dl[3] = { (size_t)g->b.ni, (size_t)g->b.nj, (size_t)g->b.nk };
    for( int d = 0; d < 3; d++ )
@@ -657,7 +660,7 @@ int sw4b200_grid_destroy( sw4b200_grid* g )
    if( !g ) return 0;
    cudaStreamSynchronize( g->st );
    double* ptrs[] = { g->U, g->Um, g->Up, g->Uacc, g->mu, g->la, g->rho, g->jac, g->met, g->d_f, g->d_rec,
-		      g->halo_buf[0], g->halo_buf[1], g->d_fser, g->d_fttser, g->d_recser };
+		      g->halo_buf[0], g->halo_buf[1], g->d_fser, g->d_fttser, g->d_recser, g->Lu };
    for( int d = 0; d < 3; d++ ) delete g->h_dc[d];
    delete g->sgd_boxes;
    for( double* p : ptrs ) if( p ) cudaFree( p );
@@ -817,8 +820,8 @@ static int upload_forces( sw4b200_grid* g, const double* h_f, int slot, double**
    return 0;
 }
 
-static int curv_predictor( sw4b200_grid* g, const double* h_f );
-static int curv_corrector( sw4b200_grid* g, const double* h_ftt );
+static int curv_predictor_dev( sw4b200_grid* g, const double* d_f );
+static int curv_corrector_dev( sw4b200_grid* g, const double* d_ftt );
 
 // the parts of the predictor / corrector that need no host data
 static int predictor_dev( sw4b200_grid* g, int part )
@@ -935,6 +938,7 @@ static int corrector_dev( sw4b200_grid* g, int part )
 // predictor of the rows of `part`: rows, then the sources lying in them
 static int predictor_part( sw4b200_grid* g, int part, const double* d_f )
 {
+   if( g->d.curvilinear ) return part == 2 ? 0 : curv_predictor_dev( g, d_f );
    if( predictor_dev( g, part ) ) return 1;
    if( !g->fast && part != 0 ) return part == 2 ? 0 : ( d_f ? inject_dev( g, d_f, g->d.dt * g->d.dt, false, 0 ) : 0 );
    return d_f ? inject_dev( g, d_f, g->d.dt * g->d.dt, g->fast, part ) : 0;
@@ -942,6 +946,7 @@ static int predictor_part( sw4b200_grid* g, int part, const double* d_f )
 // corrector of the rows of `part`: rows, F_tt at the sources lying in them, supergrid damping
 static int corrector_part( sw4b200_grid* g, int part, const double* d_ftt )
 {
+   if( g->d.curvilinear ) return part == 2 ? 0 : curv_corrector_dev( g, d_ftt );
    const double dt2 = g->d.dt * g->d.dt;
    if( corrector_dev( g, part ) ) return 1;
    if( !g->fast && part != 0 ) return part == 2 ? 0 : ( d_ftt ? inject_dev( g, d_ftt, dt2 * dt2 / 12, false, 0 ) : 0 );
@@ -951,7 +956,6 @@ static int corrector_part( sw4b200_grid* g, int part, const double* d_ftt )
 
 int sw4b200_grid_predictor( sw4b200_grid* g, const double* h_f )
 {
-   if( g->d.curvilinear ) return curv_predictor( g, h_f );
    double* d_f;
    if( upload_forces( g, h_f, 0, &d_f ) ) return 1;
    return predictor_part( g, 0, d_f );
@@ -973,23 +977,46 @@ int sw4b200_grid_enforce_bc( sw4b200_grid* g )
 
 int sw4b200_grid_corrector( sw4b200_grid* g, const double* h_ftt )
 {
-   if( g->d.curvilinear ) return curv_corrector( g, h_ftt );
    double* d_ftt;
    if( upload_forces( g, h_ftt, 1, &d_ftt ) ) return 1;
    return corrector_part( g, 0, d_ftt );
 }
 
-// curvilinear grid block: unfused sequence rhs4sgcurv -> predictor / dpdmt -> rhs4sgcurv -> corrector
-// -> addsgd4c, with Uacc as the scratch array
-static int curv_predictor( sw4b200_grid* g, const double* h_f )
+// curvilinear grid block: the reference's unfused sequence (EW.C:2569-2715) rhs4sgcurv -> predictor,
+// dpdmt -> rhs4sgcurv -> corrector -> addsgd4c, with Lu and Uacc as scratch arrays; F is injected sparsely
+static int curv_predictor_dev( sw4b200_grid* g, const double* d_f )
 {
-   (void)g; (void)h_f;
-   return set_error( "curvilinear grid blocks are not implemented yet" );
+   const double dt2 = g->d.dt * g->d.dt;
+   if( launch_rhs4sgcurv( g->b, g->U, g->mu, g->la, g->met, g->jac, g->Lu, g->d.onesided[4] == 1, g->str[0], g->str[1], g->st ) )
+      return 1;
+   if( launch_predfort( g->b, g->Up, g->U, g->Um, g->Lu, 0, g->rho, dt2, g->st ) ) return 1;
+   return d_f ? inject_dev( g, d_f, dt2, false, 0 ) : 0;
 }
-static int curv_corrector( sw4b200_grid* g, const double* h_ftt )
+static int curv_corrector_dev( sw4b200_grid* g, const double* d_ftt )
 {
-   (void)g; (void)h_ftt;
-   return set_error( "curvilinear grid blocks are not implemented yet" );
+   const double dt2 = g->d.dt * g->d.dt;
+   if( launch_dpdmt( 3 * g->b.npts, g->Up, g->U, g->Um, g->Uacc, 1.0 / dt2, g->st ) ) return 1;
+   if( launch_rhs4sgcurv( g->b, g->Uacc, g->mu, g->la, g->met, g->jac, g->Lu, g->d.onesided[4] == 1, g->str[0], g->str[1], g->st ) )
+      return 1;
+   if( launch_corrfort( g->b, g->Up, g->Lu, 0, g->rho, dt2 * dt2, g->st ) ) return 1;
+   if( d_ftt && inject_dev( g, d_ftt, dt2 * dt2 / 12, false, 0 ) ) return 1;
+   if( g->d.sg_order == 0 || g->d.beta == 0 ) return 0;
+   return launch_addsgdc( g->d.sg_order, g->b, g->Up, g->U, g->Um, g->rho, g->dc[0], g->dc[1], g->str[0], g->str[1],
+			  g->jac, g->co[0], g->co[1], g->d.beta, g->st );
+}
+
+// EW::enforceCartTopo (EW.C:3504-3531) on the new solution of the top Cartesian block and the curvilinear block
+int sw4b200_grid_enforce_cart_topo( sw4b200_grid* gcart, sw4b200_grid* gcurv )
+{
+   if( !gcart || !gcurv || gcart->d.curvilinear || !gcurv->d.curvilinear )
+      return set_error( "grid_enforce_cart_topo: needs a Cartesian block and the curvilinear block above it" );
+   if( gcart->d.corder != gcurv->d.corder ) return set_error( "grid_enforce_cart_topo: the blocks differ in layout" );
+   if( gcart->st != gcurv->st )
+   {
+      // the curvilinear block's work must be complete before the injection runs on the Cartesian block's stream
+      CUDA_OK( cudaStreamSynchronize( gcurv->st ) );
+   }
+   return launch_enforce_cart_topo( gcart->d.corder, gcart->Up, gcart->b, gcurv->Up, gcurv->b, gcart->st );
 }
 
 int sw4b200_grid_cycle( sw4b200_grid* g )
@@ -1022,7 +1049,6 @@ int sw4b200_grid_step( sw4b200_grid* g, const double* h_f, const double* h_ftt, 
 // ---- phase-split entry points for z-slab runs (the caller moves the halo planes between phases)
 int sw4b200_grid_predictor_part( sw4b200_grid* g, int part, const double* h_f )
 {
-   if( g->d.curvilinear ) return part == 2 ? 0 : curv_predictor( g, h_f );
    if( part < 0 || part > 2 ) return set_error( "predictor_part: part must be 0, 1 or 2" );
    double* d_f = g->nsrc ? g->d_f : 0;
    if( part != 2 && upload_forces( g, h_f, 0, &d_f ) ) return 1; // part 2 reuses the values uploaded by part 1
@@ -1031,7 +1057,6 @@ int sw4b200_grid_predictor_part( sw4b200_grid* g, int part, const double* h_f )
 }
 int sw4b200_grid_corrector_part( sw4b200_grid* g, int part, const double* h_ftt )
 {
-   if( g->d.curvilinear ) return part == 2 ? 0 : curv_corrector( g, h_ftt );
    if( part < 0 || part > 2 ) return set_error( "corrector_part: part must be 0, 1 or 2" );
    double* d_ftt = g->nsrc ? g->d_f + 3 * g->nsrc : 0;
    if( part != 2 && upload_forces( g, h_ftt, 1, &d_ftt ) ) return 1;
@@ -1057,7 +1082,6 @@ int sw4b200_grid_set_source_series( sw4b200_grid* g, int nsteps, const double* h
 
 int sw4b200_grid_run( sw4b200_grid* g, int first_step, int nsteps )
 {
-   if( g->d.curvilinear ) return set_error( "grid_run: curvilinear grid blocks are not implemented yet" );
    if( g->nsrc > 0 && first_step + nsteps > g->series_steps )
       return set_error( "grid_run: steps [%d,%d) exceed the uploaded source series (%d steps)", first_step,
 			first_step + nsteps, g->series_steps );

@@ -486,7 +486,7 @@ __global__ void k_predfort( Block b, double* __restrict__ up, const double* __re
       for( int c = 0; c < 3; c++ )
       {
 	 const long long q = c * b.sc + b.sp * p;
-	 up[q] = 2 * u[q] - um[q] + f * ( lu[q] + fo[q] );
+	 up[q] = 2 * u[q] - um[q] + f * ( lu[q] + ( fo ? fo[q] : 0.0 ) );
       }
    }
 }
@@ -502,7 +502,7 @@ __global__ void k_corrfort( Block b, double* __restrict__ up, const double* __re
       for( int c = 0; c < 3; c++ )
       {
 	 const long long q = c * b.sc + b.sp * p;
-	 up[q] += f * ( lu[q] + fo[q] );
+	 up[q] += f * ( lu[q] + ( fo ? fo[q] : 0.0 ) );
       }
    }
 }

@@ -72,6 +72,7 @@ SIGNATURES = {
     "sw4b200_grid_set_receiver_points": (I, [VP, I, c_ip]),
     "sw4b200_grid_predictor": (I, [VP, c_dp]),
     "sw4b200_grid_enforce_bc": (I, [VP]),
+    "sw4b200_grid_enforce_cart_topo": (I, [VP, VP]),
     "sw4b200_grid_corrector": (I, [VP, c_dp]),
     "sw4b200_grid_cycle": (I, [VP]),
     "sw4b200_grid_record": (I, [VP, c_dp]),

@@ -226,3 +226,45 @@ class GridBlock:
 
     def sync(self):
         L.check(self.lib.sw4b200_grid_sync(self.h))
+
+
+class GridStack:
+    """All grid blocks of a run that live on one device, ordered like the reference's per-grid vectors
+    (mU[g], EW.h): Cartesian grids first, the curvilinear grid under the topography last.  Sequences one
+    time step over them the way EW::timesteploop does (EW.C:2527-2842): predictor on every grid, boundary
+    conditions + the Cartesian/curvilinear interface injection (EW::enforceBC ends with enforceCartTopo,
+    EW.C:3500), corrector on every grid, boundary conditions again, cycle."""
+
+    def __init__(self, blocks, ncart=None):
+        self.blocks = list(blocks)
+        self.ncart = len(self.blocks) if ncart is None else int(ncart)
+        self.topo = self.ncart < len(self.blocks)
+        if self.topo and (self.ncart < 1 or len(self.blocks) != self.ncart + 1):
+            raise ValueError("a topography run has its Cartesian grids followed by exactly one curvilinear grid")
+        self.lib = self.blocks[0].lib
+
+    def enforce_bc(self):
+        for b in self.blocks:
+            b.enforce_bc()
+        if self.topo:
+            L.check(self.lib.sw4b200_grid_enforce_cart_topo(self.blocks[self.ncart - 1].h, self.blocks[self.ncart].h))
+
+    def step(self, f=None, ftt=None, record=False):
+        """f, ftt: per-grid lists of source amplitudes (or None)"""
+        n = len(self.blocks)
+        f = f if f is not None else [None] * n
+        ftt = ftt if ftt is not None else [None] * n
+        for g, b in enumerate(self.blocks):
+            b.predictor(f[g])
+        self.enforce_bc()
+        for g, b in enumerate(self.blocks):
+            b.corrector(ftt[g])
+        self.enforce_bc()
+        rec = [b.record() for b in self.blocks] if record else None
+        for b in self.blocks:
+            b.cycle()
+        return rec
+
+    def sync(self):
+        for b in self.blocks:
+            b.sync()
