@@ -27,6 +27,24 @@ def main():
                        f["strx"], f["stry"], f["strz"])
         out["lu_c%d" % corder] = lu
     np.savez_compressed(os.path.join(HERE, "rhs4sg_small.npz"), **out)
+    # small curvilinear case: rhs4sgcurv with the free-surface closure rows, addsgd4c, freesurfcurvisg (SoA layout)
+    from tests.test_gpu_curvilinear import curv_fields
+    dims = (12, 11, 14); seed = 61
+    box = Box(*dims)
+    f = curv_fields(box, seed, 1)
+    onesided = (0, 0, 0, 0, 1, 0)
+    lu = np.zeros(3 * box.npts)
+    refshim.rhs4sgcurv(1, box.bounds, f["u"], f["mu"], f["la"], f["met"], f["jac"], lu, onesided, acof, bope, ghcof,
+                       f["strx"], f["stry"])
+    up = f["up"].copy()
+    refshim.addsgdc(1, 4, box.bounds, up, f["u"], f["um"], f["rho"], f["dcx"], f["dcy"], f["strx"], f["stry"], f["jac"],
+                    f["cox"], f["coy"], 0.02)
+    forcing = np.random.default_rng(seed + 5).uniform(-1, 1, 3 * box.ni * box.nj)
+    ug = f["u"].copy()
+    refshim.freesurfcurvisg(1, box.bounds, box.nk - 4, 5, ug, f["mu"], f["la"], f["met"], sbop, forcing, f["strx"], f["stry"])
+    ghost = ug.reshape(3, box.nk, box.nj, box.ni)[:, 1].copy()      # plane k=0
+    np.savez_compressed(os.path.join(HERE, "curvilinear_small.npz"), dims=np.array(dims), seed=seed,
+                        lu=lu, sgd_update=up - f["up"], forcing=forcing, ghost=ghost)
     print("golden vectors written to", HERE)
 
 
