@@ -128,21 +128,30 @@ __device__ void rhs_closure_point( const A& U, const double* __restrict__ mu, co
       muq[m] = mu[plane( m + 1 )];
       laq[m] = 2 * muq[m] + la[plane( m + 1 )];
    }
+   // (zero entries of the tables are skipped: they contribute exact zeros in the reference's sums)
+#pragma unroll
    for( int q = 1; q <= 8; q++ )
    {
       double mucof = 0, lap2mu = 0;
+      bool any = false;
 #pragma unroll
       for( int m = 1; m <= 8; m++ )
       {
 	 const double a = ACOF( kb, q, m );
-	 mucof += a * muq[m - 1];
-	 lap2mu += a * laq[m - 1];
+	 if( a != 0 )
+	 {
+	    mucof += a * muq[m - 1];
+	    lap2mu += a * laq[m - 1];
+	    any = true;
+	 }
       }
+      if( !any ) continue;
       const long long pq = plane( q );
       r[0] += mucof * U( 0, pq );
       r[1] += mucof * U( 1, pq );
       r[2] += lap2mu * U( 2, pq );
    }
+   if( c_ghcof[kb - 1] != 0 )
    {
       const long long pg = plane( 0 );
       const double g = c_ghcof[kb - 1];
@@ -159,29 +168,27 @@ __device__ void rhs_closure_point( const A& U, const double* __restrict__ mu, co
    {
       const long long sa = a == 0 ? 1LL : dj;
       const double fa = a == 0 ? sx[2] : sy[2];
-      double bw[5], bu[5];
+      double bw[5] = { 0, 0, 0, 0, 0 }, bu[5] = { 0, 0, 0, 0, 0 };
+      double zmw = 0, zlu = 0;
+#pragma unroll
+      for( int q = 1; q <= 8; q++ )
+      {
+	 const double bq = sgn * BOPE( kb, q );
+	 if( bq == 0 ) continue;
+	 const long long pq = plane( q );
+	 const double wm2 = U( 2, pq - 2 * sa ), wm1 = U( 2, pq - sa ), wp1 = U( 2, pq + sa ), wp2 = U( 2, pq + 2 * sa );
+	 const double um2 = U( a, pq - 2 * sa ), um1 = U( a, pq - sa ), up1 = U( a, pq + sa ), up2 = U( a, pq + 2 * sa );
+	 bw[0] += bq * wm2; bw[1] += bq * wm1; bw[3] += bq * wp1; bw[4] += bq * wp2;
+	 bu[0] += bq * um2; bu[1] += bq * um1; bu[3] += bq * up1; bu[4] += bq * up2;
+	 zmw += bq * ( muq[q - 1] * d0( wm2, wm1, wp1, wp2 ) );
+	 zlu += bq * ( la[pq] * d0( um2, um1, up1, up2 ) );
+      }
 #pragma unroll
       for( int m = 0; m < 5; m++ )
       {
-	 bw[m] = bu[m] = 0;
 	 if( m == 2 ) continue;
-	 for( int q = 1; q <= 8; q++ )
-	 {
-	    const long long pq = plane( q ) + ( m - 2 ) * sa;
-	    const double bq = sgn * BOPE( kb, q );
-	    bw[m] += bq * U( 2, pq );
-	    bu[m] += bq * U( a, pq );
-	 }
 	 bw[m] *= la[p + ( m - 2 ) * sa];
 	 bu[m] *= mu[p + ( m - 2 ) * sa];
-      }
-      double zmw = 0, zlu = 0;
-      for( int q = 1; q <= 8; q++ )
-      {
-	 const long long pq = plane( q );
-	 const double bq = sgn * BOPE( kb, q );
-	 zmw += bq * ( muq[q - 1] * d0( U( 2, pq - 2 * sa ), U( 2, pq - sa ), U( 2, pq + sa ), U( 2, pq + 2 * sa ) ) );
-	 zlu += bq * ( la[pq] * d0( U( a, pq - 2 * sa ), U( a, pq - sa ), U( a, pq + sa ), U( a, pq + 2 * sa ) ) );
       }
       r[a] += fa * ( d0( bw[0], bw[1], bw[3], bw[4] ) + zmw );
       r[2] += fa * ( d0( bu[0], bu[1], bu[3], bu[4] ) + zlu );
