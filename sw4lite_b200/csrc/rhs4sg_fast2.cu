@@ -34,7 +34,8 @@ struct Cfg
    static constexpr int NPT = ( PLANE + NT - 1 ) / NT;
    static constexpr int NH = 4 * TY + 4 * TX; // helper (ring) points per plane
    static constexpr int EX = 3 * TY * PX, EY = 3 * PY * TX;
-   static constexpr int SMEM_DOUBLES = 5 * NSLOT * PLANE + 2 * ( EX + EY ) + PX + PY;
+   static constexpr int OPS = 4 * NT; // epilogue operands of one plane: rho, um[3] of the own points
+   static constexpr int SMEM_DOUBLES = 5 * NSLOT * PLANE + 2 * ( EX + EY ) + PX + PY + 2 * OPS;
 };
 
 // per-thread register state.  6-rings: plane q lives at physical index (q - p0) % 6 (5 planes are
@@ -46,14 +47,15 @@ struct State
    double dyv[3], dyu[3], dxv[3], dxu[3]; // in-plane first differences
    double muk[3], lak[3];
    double rp[3];			  // result of the previous plane, still lacking the exchanged cross terms
-   double szq;				  // strz of that plane
+   double sz[6];			  // strz of the planes in the ring
+   double szn;				  // strz of the next plane (loaded one step ahead)
 };
 
 template <int TY>
 struct Ctx
 {
    typedef Cfg<TY> C;
-   double *s_f, *s_ex, *s_ey, *s_sx, *s_sy;
+   double *s_f, *s_ex, *s_ey, *s_sx, *s_sy, *s_op;
    int goff[C::NPT];
    bool inb[C::NPT];
    int tid, tx, ty, o;
@@ -63,17 +65,32 @@ struct Ctx
    double sx, sy, sxm2, sxm1, sxp1, sxp2, sym2, sym1, syp1, syp2;
 };
 
-template <int TY>
-__device__ __forceinline__ void stage( const FastArgs& a, const Ctx<TY>& c, int p, int slot )
+// stage plane p into ring slot `slot`; with an epilogue also the own-point operands (rho, um) of plane p-3,
+// the plane that the step handling plane p finishes, into operand buffer `ob`
+template <int TY, int EPI>
+__device__ __forceinline__ void stage( const FastArgs& a, const Ctx<TY>& c, int p, int slot, int ob )
 {
    typedef Cfg<TY> C;
+   if( p > c.pend + 1 ) return;
+   if( EPI != EPI_LU )
+   {
+      const int kq = p - 3;
+      if( c.act && kq >= c.ka && kq <= c.kb )
+      {
+	 const long long q = a.b.nij * ( kq - a.b.kfirst ) + c.gown;
+	 double* const d = c.s_op + ob * C::OPS + c.tid;
+	 cp_async8( d, a.rho + q, true );
+#pragma unroll
+	 for( int m = 0; m < 3; m++ ) cp_async8( d + ( m + 1 ) * C::NT, a.um[m] + q, true );
+      }
+   }
    const long long koff = a.b.nij * ( p - a.b.kfirst );
    const double* const gsrc[5] = { a.u[0], a.u[1], a.u[2], a.mu, a.la };
 #pragma unroll
    for( int q = 0; q < C::NPT; q++ )
    {
       const int idx = c.tid + q * C::NT;
-      if( idx < C::PLANE )
+      if( idx < C::PLANE && p <= c.pend ) // (the step after the last plane only finishes plane kb)
       {
 #pragma unroll
 	 for( int f = 0; f < 5; f++ )
@@ -100,21 +117,16 @@ __device__ __forceinline__ void step( const FastArgs& a, Ctx<TY>& c, State& s, c
 
    cp_async_wait_all();
    __syncthreads(); // plane p and the E products of plane k-1 are visible; slot of plane p-5 is free
-   if( p + 1 <= c.pend ) stage<TY>( a, c, p + 1, ( S + 1 ) % NSLOT );
+   stage<TY, EPI>( a, c, p + 1, ( S + 1 ) % NSLOT, ( S + 1 ) & 1 );
 
-   // epilogue operands of plane kf: issue the global loads early (a safe address when nothing is stored)
+   // epilogue operands of plane kf (staged one step ago by this thread itself); dense forcing, if any, from global
    const bool fin = c.act && kf >= c.ka && kf <= c.kb;
    const long long qf = fin ? b.nij * ( kf - b.kfirst ) + c.gown : 0;
-   double e_rho = 1, e_um[3] = { 0, 0, 0 }, e_fo[3] = { 0, 0, 0 };
-   if( EPI != EPI_LU )
+   double e_fo[3] = { 0, 0, 0 };
+   if( EPI != EPI_LU && a.fo[0] )
    {
-      e_rho = a.rho[qf];
 #pragma unroll
-      for( int m = 0; m < 3; m++ )
-      {
-	 e_um[m] = a.um[m][qf];
-	 if( a.fo[0] ) e_fo[m] = a.fo[m][qf];
-      }
+      for( int m = 0; m < 3; m++ ) e_fo[m] = a.fo[m][qf];
    }
 
    const double sx = c.sx, sy = c.sy;
@@ -126,9 +138,11 @@ __device__ __forceinline__ void step( const FastArgs& a, Ctx<TY>& c, State& s, c
       const double* const pm = c.s_f + ( 3 * NSLOT + S ) * PLANE + c.o;
       const double* const pl = c.s_f + ( 4 * NSLOT + S ) * PLANE + c.o;
       const double u0 = pu[0], v0 = pv[0], w0 = pw[0], m0 = pm[0], l0 = pl[0];
-      int kp = p - b.kfirst;
+      const double szp = s.szn; // strz(p), loaded during the previous step
+      s.sz[R0] = szp;
+      int kp = p + 1 - b.kfirst;
       kp = kp > b.nk - 1 ? b.nk - 1 : kp;
-      const double szp = a.strz[kp];
+      s.szn = a.strz[kp];
       s.cu[R0] = u0; s.cv[R0] = v0; s.cw[R0] = w0;
       s.amz[R0] = m0 * szp; s.alz[R0] = ( 2 * m0 + l0 ) * szp;
       s.muk[T0] = m0; s.lak[T0] = l0;
@@ -164,9 +178,7 @@ __device__ __forceinline__ void step( const FastArgs& a, Ctx<TY>& c, State& s, c
    }
 
    // ---- z pieces of plane k and its exchanged products
-   int kk = k - b.kfirst;
-   kk = kk < 0 ? 0 : ( kk > b.nk - 1 ? b.nk - 1 : kk );
-   const double szk = a.strz[kk];
+   const double szk = s.sz[R2];
    double rnew[3];
    {
       const W4 wmz = weights4( s.amz[R4], s.amz[R3], s.amz[R2], s.amz[R1], s.amz[R0] );
@@ -251,10 +263,17 @@ __device__ __forceinline__ void step( const FastArgs& a, Ctx<TY>& c, State& s, c
       const double y1 = d0u( ey[-2 * TX], ey[-TX], ey[TX], ey[2 * TX] );
       const double y2 = d0u( ey[PY * TX - 2 * TX], ey[PY * TX - TX], ey[PY * TX + TX], ey[PY * TX + 2 * TX] );
       const double y3 = d0u( ey[2 * PY * TX - 2 * TX], ey[2 * PY * TX - TX], ey[2 * PY * TX + TX], ey[2 * PY * TX + 2 * TX] );
+      double e_rho = 1, e_um[3] = { 0, 0, 0 };
+      if( EPI != EPI_LU )
+      {
+	 const double* const d = c.s_op + ( S & 1 ) * C::OPS + c.tid;
+	 e_rho = d[0];
+	 e_um[0] = d[NT]; e_um[1] = d[2 * NT]; e_um[2] = d[3 * NT];
+      }
       double r[3];
       r[0] = s.rp[0] + ( a.cof144 * sx ) * ( x1 + sy * y1 );
       r[1] = s.rp[1] + ( a.cof144 * sy ) * ( sx * x2 + y2 );
-      r[2] = s.rp[2] + ( a.cof144 * s.szq ) * ( sx * x3 + sy * y3 );
+      r[2] = s.rp[2] + ( a.cof144 * s.sz[R3] ) * ( sx * x3 + sy * y3 );
       if( fin )
       {
 	 if( EPI == EPI_LU )
@@ -284,7 +303,6 @@ __device__ __forceinline__ void step( const FastArgs& a, Ctx<TY>& c, State& s, c
       }
    }
    s.rp[0] = rnew[0]; s.rp[1] = rnew[1]; s.rp[2] = rnew[2];
-   s.szq = szk;
 }
 
 } // namespace fast2
@@ -302,6 +320,7 @@ __global__ void __launch_bounds__( 32 * TY, 1 ) k_rhs_fast2( const FastArgs a )
    c.s_ey = c.s_ex + 2 * C::EX;			    // [2][3][PY][TX]  E4..E6
    c.s_sx = c.s_ey + 2 * C::EY;			    // [PX] strx of the tile columns incl. ring
    c.s_sy = c.s_sx + PX;			    // [PY]
+   c.s_op = c.s_sy + PY;			    // [2][4][NT] rho, um of the own points of the plane being finished
 
    const Block& b = a.b;
    c.tx = threadIdx.x; c.ty = threadIdx.y; c.tid = c.ty * TX + c.tx;
@@ -340,7 +359,7 @@ __global__ void __launch_bounds__( 32 * TY, 1 ) k_rhs_fast2( const FastArgs a )
 
    fast2::State s;
 #pragma unroll
-   for( int m = 0; m < 6; m++ ) s.cu[m] = s.cv[m] = s.cw[m] = s.amz[m] = s.alz[m] = s.g1[m] = s.g2[m] = s.g3[m] = 0;
+   for( int m = 0; m < 6; m++ ) s.cu[m] = s.cv[m] = s.cw[m] = s.amz[m] = s.alz[m] = s.g1[m] = s.g2[m] = s.g3[m] = s.sz[m] = 0;
 #pragma unroll
    for( int m = 0; m < 3; m++ )
    {
@@ -348,14 +367,13 @@ __global__ void __launch_bounds__( 32 * TY, 1 ) k_rhs_fast2( const FastArgs a )
       s.dyv[m] = s.dyu[m] = s.dxv[m] = s.dxu[m] = s.muk[m] = s.lak[m] = 0;
       s.rp[m] = 0;
    }
-   s.szq = 0;
-
    int p = c.ka - 2;
+   s.szn = a.strz[p - b.kfirst];
    const int plast = c.kb + 3; // one extra step finishes plane kb
    {
       int ph0 = p % 6;
       ph0 = ph0 < 0 ? ph0 + 6 : ph0;
-      fast2::stage<TY>( a, c, p, ph0 );
+      fast2::stage<TY, EPI>( a, c, p, ph0, ph0 & 1 );
    }
    __syncthreads(); // s_sx, s_sy visible
    c.sx = c.s_sx[c.tx + 2]; c.sy = c.s_sy[c.ty + 2];
