@@ -176,3 +176,34 @@ def test_slabs_on_one_gpu_reproduce_single_block(nslabs):
         k0 = s.bounds[4] - whole.bounds[4]
         own = s.download("U").reshape(3, s.nk, nij)[:, 2:-2]
         assert np.array_equal(own, ref[:, k0 + 2:k0 + s.nk - 2]), "slab at k0=%d" % s.bounds[4]
+
+
+@needs_ref
+def test_loh1_h100_station_matches_golden(tmp_path):
+    """config 3: LOH.1 layer over half-space (tests/loh1/LOH.1-h100.in: 301x301x171, free surface, supergrid
+    gp=30 on five sides, three material blocks, Gaussian moment source, 536 steps).  The reference's set-up
+    (parser, materials, supergrid arrays, source discretisation, time functions) feeds the device block, which
+    runs all steps device-resident; the station trace must reproduce the reference's golden sta10.txt
+    (tests/loh1/loh1-h100-sta10/sta10.txt; the reference's own builds differ from it at the 1e-14 level)."""
+    ew = refshim.RefEW(os.path.join(INPUTS, "LOH.1-h100.in"), str(tmp_path))
+    assert ew.ngrids == 1 and ew.corder == 1 and ew.nsteps == 536
+    blk = block_from_reference(ew)
+    src = SourceMap(ew)
+    blk.set_source_points(src.points)
+    recs, _ = ew.receivers()
+    assert len(recs) == 1
+    blk.set_receiver_points(np.array([recs[0][1:4]], dtype=np.int32))
+    n = ew.nsteps
+    times = ew.tstart + ew.dt * np.arange(n)
+    f_all = np.array([src.reduce(ew.eval_forces(t, False)) for t in times])
+    ftt_all = np.array([src.reduce(ew.eval_forces(t, True)) for t in times])
+    blk.set_source_series(f_all, ftt_all)
+    blk.run(0, n)
+    trace = blk.fetch_records(0, n)[:, 0, :]
+    gold = np.array([l.split() for l in open(os.path.join(os.path.dirname(__file__), "golden", "loh1-h100-sta10", "sta10.txt"))
+                     if not l.startswith("#")], dtype=np.float64)
+    assert gold.shape[0] == n + 1
+    scale = np.abs(gold[:, 1:4]).max()
+    err = np.abs(trace - gold[1:, 1:4]).max() / scale
+    print("LOH.1-h100 sta10: max rel. diff to the golden trace %.3g (amplitude %.3g)" % (err, scale))
+    assert scale > 0 and err < 1e-9
