@@ -35,7 +35,8 @@ struct Cfg
    static constexpr int NH = 4 * TY + 4 * TX; // helper (ring) points per plane
    static constexpr int EX = 3 * TY * PX, EY = 3 * PY * TX;
    static constexpr int OPS = 4 * NT; // epilogue operands of one plane: rho, um[3] of the own points
-   static constexpr int SMEM_DOUBLES = 5 * NSLOT * PLANE + 2 * ( EX + EY ) + PX + PY + 2 * OPS;
+   static constexpr int SZMAX = 1024; // strz of the planes a CTA marches through (kchunk + 6 <= SZMAX)
+   static constexpr int SMEM_DOUBLES = 5 * NSLOT * PLANE + 2 * ( EX + EY ) + PX + PY + 2 * OPS + SZMAX;
 };
 
 // per-thread register state.  6-rings: plane q lives at physical index (q - p0) % 6 (5 planes are
@@ -47,15 +48,14 @@ struct State
    double dyv[3], dyu[3], dxv[3], dxu[3]; // in-plane first differences
    double muk[3], lak[3];
    double rp[3];			  // result of the previous plane, still lacking the exchanged cross terms
-   double sz[6];			  // strz of the planes in the ring
-   double szn;				  // strz of the next plane (loaded one step ahead)
 };
 
 template <int TY>
 struct Ctx
 {
    typedef Cfg<TY> C;
-   double *s_f, *s_ex, *s_ey, *s_sx, *s_sy, *s_op;
+   double *s_f, *s_ex, *s_ey, *s_sx, *s_sy, *s_op, *s_sz;
+   int p0;
    int goff[C::NPT];
    bool inb[C::NPT];
    int tid, tx, ty, o;
@@ -138,11 +138,7 @@ __device__ __forceinline__ void step( const FastArgs& a, Ctx<TY>& c, State& s, c
       const double* const pm = c.s_f + ( 3 * NSLOT + S ) * PLANE + c.o;
       const double* const pl = c.s_f + ( 4 * NSLOT + S ) * PLANE + c.o;
       const double u0 = pu[0], v0 = pv[0], w0 = pw[0], m0 = pm[0], l0 = pl[0];
-      const double szp = s.szn; // strz(p), loaded during the previous step
-      s.sz[R0] = szp;
-      int kp = p + 1 - b.kfirst;
-      kp = kp > b.nk - 1 ? b.nk - 1 : kp;
-      s.szn = a.strz[kp];
+      const double szp = c.s_sz[p - c.p0];
       s.cu[R0] = u0; s.cv[R0] = v0; s.cw[R0] = w0;
       s.amz[R0] = m0 * szp; s.alz[R0] = ( 2 * m0 + l0 ) * szp;
       s.muk[T0] = m0; s.lak[T0] = l0;
@@ -178,7 +174,7 @@ __device__ __forceinline__ void step( const FastArgs& a, Ctx<TY>& c, State& s, c
    }
 
    // ---- z pieces of plane k and its exchanged products
-   const double szk = s.sz[R2];
+   const double szk = k >= c.p0 ? c.s_sz[k - c.p0] : 0.0;
    double rnew[3];
    {
       const W4 wmz = weights4( s.amz[R4], s.amz[R3], s.amz[R2], s.amz[R1], s.amz[R0] );
@@ -273,7 +269,7 @@ __device__ __forceinline__ void step( const FastArgs& a, Ctx<TY>& c, State& s, c
       double r[3];
       r[0] = s.rp[0] + ( a.cof144 * sx ) * ( x1 + sy * y1 );
       r[1] = s.rp[1] + ( a.cof144 * sy ) * ( sx * x2 + y2 );
-      r[2] = s.rp[2] + ( a.cof144 * s.sz[R3] ) * ( sx * x3 + sy * y3 );
+      r[2] = s.rp[2] + ( a.cof144 * ( kf >= c.p0 ? c.s_sz[kf - c.p0] : 0.0 ) ) * ( sx * x3 + sy * y3 );
       if( fin )
       {
 	 if( EPI == EPI_LU )
@@ -321,6 +317,7 @@ __global__ void __launch_bounds__( 32 * TY, 1 ) k_rhs_fast2( const FastArgs a )
    c.s_sx = c.s_ey + 2 * C::EY;			    // [PX] strx of the tile columns incl. ring
    c.s_sy = c.s_sx + PX;			    // [PY]
    c.s_op = c.s_sy + PY;			    // [2][4][NT] rho, um of the own points of the plane being finished
+   c.s_sz = c.s_op + 2 * C::OPS;		    // [SZMAX] strz of planes ka-2 .. kb+3
 
    const Block& b = a.b;
    c.tx = threadIdx.x; c.ty = threadIdx.y; c.tid = c.ty * TX + c.tx;
@@ -352,6 +349,13 @@ __global__ void __launch_bounds__( 32 * TY, 1 ) k_rhs_fast2( const FastArgs a )
 	 c.s_sy[t - PX] = lj < b.nj ? a.stry[lj] : 0.0;
       }
    }
+   c.p0 = c.ka - 2;
+   for( int t = c.tid; t <= c.kb + 3 - c.p0; t += NT )
+   {
+      int kp = c.p0 + t - b.kfirst;
+      kp = kp > b.nk - 1 ? b.nk - 1 : kp;
+      c.s_sz[t] = a.strz[kp];
+   }
    c.o = ( c.ty + 2 ) * PX + c.tx + 2; // own point in a staged plane
    const int li = li0 + c.tx, lj = lj0 + c.ty;
    c.act = li <= b.ni - 3 && lj <= b.nj - 3;
@@ -359,7 +363,7 @@ __global__ void __launch_bounds__( 32 * TY, 1 ) k_rhs_fast2( const FastArgs a )
 
    fast2::State s;
 #pragma unroll
-   for( int m = 0; m < 6; m++ ) s.cu[m] = s.cv[m] = s.cw[m] = s.amz[m] = s.alz[m] = s.g1[m] = s.g2[m] = s.g3[m] = s.sz[m] = 0;
+   for( int m = 0; m < 6; m++ ) s.cu[m] = s.cv[m] = s.cw[m] = s.amz[m] = s.alz[m] = s.g1[m] = s.g2[m] = s.g3[m] = 0;
 #pragma unroll
    for( int m = 0; m < 3; m++ )
    {
@@ -368,7 +372,6 @@ __global__ void __launch_bounds__( 32 * TY, 1 ) k_rhs_fast2( const FastArgs a )
       s.rp[m] = 0;
    }
    int p = c.ka - 2;
-   s.szn = a.strz[p - b.kfirst];
    const int plast = c.kb + 3; // one extra step finishes plane kb
    {
       int ph0 = p % 6;
@@ -428,6 +431,7 @@ int launch_fast2( int epi, FastArgs a, cudaStream_t st )
 {
    if( a.khi < a.klo ) return 0;
    if( a.kchunk <= 0 ) a.kchunk = fast_kchunk( a.b, a.khi - a.klo + 1, 8 );
+   if( a.kchunk > fast2::Cfg<8>::SZMAX - 6 ) a.kchunk = fast2::Cfg<8>::SZMAX - 6;
    switch( epi )
    {
    case EPI_LU: return launch_fast2_t<8, EPI_LU>( a, st );
