@@ -374,6 +374,13 @@ int sw4b200_copy_stencilcoefficients( const double* acof, const double* ghcof, c
    CUDA_OK( cudaMemcpyToSymbol( c_ghcof, ghcof, 6 * sizeof( double ) ) );
    CUDA_OK( cudaMemcpyToSymbol( c_bope, bope, 48 * sizeof( double ) ) );
    CUDA_OK( cudaMemcpyToSymbol( c_sbop, sbop, 5 * sizeof( double ) ) );
+   {
+      // the throughput closure kernel has the built-in tables folded in; other tables take the general kernel
+      double a0[384], g0[6], b0[48], s0[5];
+      builtin_coefficients( a0, g0, b0, s0 );
+      g_builtin_sbp_tables = memcmp( a0, acof, sizeof( a0 ) ) == 0 && memcmp( g0, ghcof, sizeof( g0 ) ) == 0 &&
+			     memcmp( b0, bope, sizeof( b0 ) ) == 0;
+   }
    return 0;
 }
 

@@ -7,6 +7,8 @@
 // Reference semantics: rhs4sg.C:38-849 / rhs4sg_rev.C:44-864 (L(u)), ew-cfromfort.C:40-141
 // (corrector, predictor, dpdmt), :748-1160 (supergrid damping), :205-745 (bcfortsg).
 #include "common.cuh"
+#include "sbp4_constexpr.h"
+#include <cstdlib>
 
 namespace sw4b200 {
 
@@ -394,6 +396,287 @@ __global__ void __launch_bounds__( CL_TX* CL_TY ) k_closure_staged( RhsArgs a, i
    }
 }
 
+// SBP closure rows, second version: the staged planes as above, but the operator is evaluated like the
+// interior throughput kernel (rhs4sg_fast2.cu) -- every in-plane piece once per point, the 12 cross terms from
+// 6 exchanged products per point, differenced through shared memory -- with the z pieces replaced by the
+// one-sided sums of the closure (rhs4sg_rev.C:349-855): G_z -> sum_q [sum_m acof(k,q,m) a(m)] u(q) + ghcof(k) a(1) u(0),
+// D0z -> +-sum_q bope(k,q) . (q), no strz, no 1/6.  Zero table entries are skipped.  One thread per column of a
+// 32x8 tile, rows kb_lo..kb_hi of one side.  Agrees with rhs_closure_point to rounding (different association).
+constexpr int CF_EX = 3 * CL_TY * CL_PX, CF_EY = 3 * CL_PY * CL_TX;
+constexpr int CF_OPS = 6 * 4 * CL_TX * CL_TY; // epilogue operands (rho, um or up) of the own points of the 6 rows
+constexpr int CF_SMEM_DOUBLES = 5 * CL_NP * CL_PLANE + CF_EX + CF_EY + CL_PX + CL_PY + CF_OPS;
+
+__device__ __forceinline__ void cf_cp_async8( double* sdst, const double* gsrc, bool valid )
+{
+   const unsigned d = (unsigned)__cvta_generic_to_shared( sdst );
+   const int sz = valid ? 8 : 0;
+   asm volatile( "cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"( d ), "l"( gsrc ), "r"( sz ) : "memory" );
+}
+
+__device__ __forceinline__ double cf_d0u( double fm2, double fm1, double fp1, double fp2 )
+{
+   return ( fm2 - fp2 ) + 8 * ( fp1 - fm1 ); // 12 * centred first difference
+}
+
+template <int MODE>
+__global__ void __launch_bounds__( CL_TX* CL_TY, 1 ) k_closure_fast( RhsArgs a, int side, int kb_lo, int kb_hi )
+{
+   extern __shared__ double sm[];
+   constexpr int TX = CL_TX, TY = CL_TY, PX = CL_PX, PY = CL_PY, PLANE = CL_PLANE, NP = CL_NP, NT = CL_TX * CL_TY;
+   double* const s_f = sm;				 // [5 fields][9 planes][PLANE]
+   double* const s_ex = sm + 5 * NP * PLANE;		 // [3][TY][PX]
+   double* const s_ey = s_ex + CF_EX;			 // [3][PY][TX]
+   double* const s_sx = s_ey + CF_EY;			 // [PX]
+   double* const s_sy = s_sx + PX;			 // [PY]
+   double* const s_op = s_sy + PY;			 // [6 rows][4][NT]
+   constexpr bool STAGED_OPS = MODE == MODE_PRED || MODE == MODE_CORR_ACC;
+   const Block& b = a.b;
+   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
+   const int li0 = 2 + blockIdx.x * TX, lj0 = 2 + blockIdx.y * TY;
+   const int kbase = side == 0 ? 0 : a.nk - 7; // global k of staged plane 0
+   if( STAGED_OPS && li0 + tx <= b.ni - 3 && lj0 + ty <= b.nj - 3 )
+   {
+      // epilogue operands of the thread's own points: in flight together with the planes
+      for( int kb = kb_lo; kb <= kb_hi; kb++ )
+      {
+	 const int k = side == 0 ? kb : a.nk - kb + 1;
+	 const long long p = (long long)( li0 + tx ) + (long long)b.ni * ( lj0 + ty ) + b.nij * ( k - b.kfirst );
+	 double* const d = s_op + ( kb - 1 ) * 4 * NT + tid;
+	 cf_cp_async8( d, a.rho + p, true );
+	 const double* const src = MODE == MODE_PRED ? a.um : a.up;
+#pragma unroll
+	 for( int c = 0; c < 3; c++ ) cf_cp_async8( d + ( c + 1 ) * NT, src + c * b.sc + b.sp * p, true );
+      }
+   }
+   const double dt2i = 1.0 / ( a.dt * a.dt );
+   for( int idx = tid; idx < PLANE; idx += NT )
+   {
+      const int sy_ = idx / PX, sx_ = idx - sy_ * PX;
+      const int li = li0 - 2 + sx_, lj = lj0 - 2 + sy_;
+      const bool inb = li < b.ni && lj < b.nj;
+#pragma unroll
+      for( int s = 0; s < NP; s++ )
+      {
+	 const long long p = inb ? (long long)li + (long long)b.ni * lj + b.nij * ( kbase + s - b.kfirst ) : 0;
+	 if( MODE == MODE_CORR )
+	 {
+#pragma unroll
+	    for( int c = 0; c < 3; c++ )
+	    {
+	       const long long q = c * b.sc + b.sp * p;
+	       s_f[( c * NP + s ) * PLANE + idx] = inb ? dt2i * ( a.up[q] - 2 * a.u[q] + a.um[q] ) : 0.0;
+	    }
+	    s_f[( 3 * NP + s ) * PLANE + idx] = inb ? a.mu[p] : 0.0;
+	    s_f[( 4 * NP + s ) * PLANE + idx] = inb ? a.la[p] : 0.0;
+	 }
+	 else
+	 {
+	    // asynchronous copies: all 45 values of the column are in flight at once (zero fill outside the block)
+#pragma unroll
+	    for( int c = 0; c < 3; c++ ) cf_cp_async8( s_f + ( c * NP + s ) * PLANE + idx, a.u + c * b.sc + b.sp * p, inb );
+	    cf_cp_async8( s_f + ( 3 * NP + s ) * PLANE + idx, a.mu + p, inb );
+	    cf_cp_async8( s_f + ( 4 * NP + s ) * PLANE + idx, a.la + p, inb );
+	 }
+      }
+   }
+   if( MODE != MODE_CORR ) asm volatile( "cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory" );
+   for( int t = tid; t < PX + PY; t += NT )
+   {
+      if( t < PX ) { const int li = li0 - 2 + t; s_sx[t] = li < b.ni ? a.strx[li] : 0.0; }
+      else { const int lj = lj0 - 2 + ( t - PX ); s_sy[t - PX] = lj < b.nj ? a.stry[lj] : 0.0; }
+   }
+   __syncthreads();
+   // closure row q (1..8; 0 = ghost plane) lives in staged plane q (low side) or 8-q (high side)
+   const int pbase = side == 0 ? 0 : 8 * PLANE, pstr = side == 0 ? PLANE : -PLANE;
+   const double sgn = side == 0 ? 1.0 : -1.0;
+   const int o = ( ty + 2 ) * PX + tx + 2;
+   const int li = li0 + tx, lj = lj0 + ty;
+   const bool act = li <= b.ni - 3 && lj <= b.nj - 3;
+   const double sx = s_sx[tx + 2], sy = s_sy[ty + 2];
+   const double sxm2 = s_sx[tx], sxm1 = s_sx[tx + 1], sxp1 = s_sx[tx + 3], sxp2 = s_sx[tx + 4];
+   const double sym2 = s_sy[ty], sym1 = s_sy[ty + 1], syp1 = s_sy[ty + 3], syp2 = s_sy[ty + 4];
+   auto F = [&]( int f, int q, int off ) { return s_f[f * NP * PLANE + pbase + q * pstr + off]; };
+
+   // column data shared by all rows: coefficients and the z-differenced in-plane products of rows 1..8
+   double muq[8], l2q[8], g1[8], g2[8], g3[8];
+#pragma unroll
+   for( int q = 1; q <= 8; q++ )
+   {
+      const double m = F( 3, q, o ), l = F( 4, q, o );
+      muq[q - 1] = m;
+      l2q[q - 1] = 2 * m + l;
+      const double dxw = cf_d0u( F( 2, q, o - 2 ), F( 2, q, o - 1 ), F( 2, q, o + 1 ), F( 2, q, o + 2 ) );
+      const double dyw = cf_d0u( F( 2, q, o - 2 * PX ), F( 2, q, o - PX ), F( 2, q, o + PX ), F( 2, q, o + 2 * PX ) );
+      const double dxu = cf_d0u( F( 0, q, o - 2 ), F( 0, q, o - 1 ), F( 0, q, o + 1 ), F( 0, q, o + 2 ) );
+      const double dyv = cf_d0u( F( 1, q, o - 2 * PX ), F( 1, q, o - PX ), F( 1, q, o + PX ), F( 1, q, o + 2 * PX ) );
+      g1[q - 1] = m * dxw;
+      g2[q - 1] = m * dyw;
+      g3[q - 1] = l * ( sx * dxu + sy * dyv );
+   }
+   const double cof = 1.0 / ( a.h * a.h );
+#pragma unroll
+   for( int kb = 1; kb <= 6; kb++ )
+   {
+      if( kb < kb_lo || kb > kb_hi ) continue; // uniform
+      // ---- in-plane pieces of row kb
+      const double u0 = F( 0, kb, o ), v0 = F( 1, kb, o ), w0 = F( 2, kb, o ), m0 = muq[kb - 1], l0 = F( 4, kb, o );
+      const double uxm2 = F( 0, kb, o - 2 ), uxm1 = F( 0, kb, o - 1 ), uxp1 = F( 0, kb, o + 1 ), uxp2 = F( 0, kb, o + 2 );
+      const double vxm2 = F( 1, kb, o - 2 ), vxm1 = F( 1, kb, o - 1 ), vxp1 = F( 1, kb, o + 1 ), vxp2 = F( 1, kb, o + 2 );
+      const double wxm2 = F( 2, kb, o - 2 ), wxm1 = F( 2, kb, o - 1 ), wxp1 = F( 2, kb, o + 1 ), wxp2 = F( 2, kb, o + 2 );
+      const double uym2 = F( 0, kb, o - 2 * PX ), uym1 = F( 0, kb, o - PX ), uyp1 = F( 0, kb, o + PX ), uyp2 = F( 0, kb, o + 2 * PX );
+      const double vym2 = F( 1, kb, o - 2 * PX ), vym1 = F( 1, kb, o - PX ), vyp1 = F( 1, kb, o + PX ), vyp2 = F( 1, kb, o + 2 * PX );
+      const double wym2 = F( 2, kb, o - 2 * PX ), wym1 = F( 2, kb, o - PX ), wyp1 = F( 2, kb, o + PX ), wyp2 = F( 2, kb, o + 2 * PX );
+      const double dxu = cf_d0u( uxm2, uxm1, uxp1, uxp2 ), dxv = cf_d0u( vxm2, vxm1, vxp1, vxp2 );
+      const double dyu = cf_d0u( uym2, uym1, uyp1, uyp2 ), dyv = cf_d0u( vym2, vym1, vyp1, vyp2 );
+      double pr[3];
+      {
+	 const double mxm2 = F( 3, kb, o - 2 ), mxm1 = F( 3, kb, o - 1 ), mxp1 = F( 3, kb, o + 1 ), mxp2 = F( 3, kb, o + 2 );
+	 const double lxm2 = F( 4, kb, o - 2 ), lxm1 = F( 4, kb, o - 1 ), lxp1 = F( 4, kb, o + 1 ), lxp2 = F( 4, kb, o + 2 );
+	 const double mym2 = F( 3, kb, o - 2 * PX ), mym1 = F( 3, kb, o - PX ), myp1 = F( 3, kb, o + PX ), myp2 = F( 3, kb, o + 2 * PX );
+	 const double lym2 = F( 4, kb, o - 2 * PX ), lym1 = F( 4, kb, o - PX ), lyp1 = F( 4, kb, o + PX ), lyp2 = F( 4, kb, o + 2 * PX );
+	 const double amx[5] = { mxm2 * sxm2, mxm1 * sxm1, m0 * sx, mxp1 * sxp1, mxp2 * sxp2 };
+	 const double alx[5] = { ( 2 * mxm2 + lxm2 ) * sxm2, ( 2 * mxm1 + lxm1 ) * sxm1, ( 2 * m0 + l0 ) * sx,
+				 ( 2 * mxp1 + lxp1 ) * sxp1, ( 2 * mxp2 + lxp2 ) * sxp2 };
+	 const double amy[5] = { mym2 * sym2, mym1 * sym1, m0 * sy, myp1 * syp1, myp2 * syp2 };
+	 const double aly[5] = { ( 2 * mym2 + lym2 ) * sym2, ( 2 * mym1 + lym1 ) * sym1, ( 2 * m0 + l0 ) * sy,
+				 ( 2 * myp1 + lyp1 ) * syp1, ( 2 * myp2 + lyp2 ) * syp2 };
+	 double wmx[4], wlx[4], wmy[4], wly[4];
+	 weights4( amx, wmx ); weights4( alx, wlx ); weights4( amy, wmy ); weights4( aly, wly );
+	 const double fxu[5] = { uxm2, uxm1, u0, uxp1, uxp2 }, fxv[5] = { vxm2, vxm1, v0, vxp1, vxp2 }, fxw[5] = { wxm2, wxm1, w0, wxp1, wxp2 };
+	 const double fyu[5] = { uym2, uym1, u0, uyp1, uyp2 }, fyv[5] = { vym2, vym1, v0, vyp1, vyp2 }, fyw[5] = { wym2, wym1, w0, wyp1, wyp2 };
+	 pr[0] = sx * gsum( wlx, fxu ) + sy * gsum( wmy, fyu );
+	 pr[1] = sx * gsum( wmx, fxv ) + sy * gsum( wly, fyv );
+	 pr[2] = sx * gsum( wmx, fxw ) + sy * gsum( wmy, fyw );
+      }
+      // ---- one-sided z pieces
+      double rz[3] = { 0, 0, 0 }, bz[3] = { 0, 0, 0 }, t[3] = { 0, 0, 0 };
+#pragma unroll
+      for( int q = 1; q <= 8; q++ )
+      {
+	 double mc = 0, lc = 0;
+	 bool any = false;
+#pragma unroll
+	 for( int m = 1; m <= 8; m++ )
+	 {
+	    const double ac = acof_c( ( kb - 1 ) + 6 * ( q - 1 ) + 48 * ( m - 1 ) );
+	    if( ac != 0 ) { mc += ac * muq[m - 1]; lc += ac * l2q[m - 1]; any = true; }
+	 }
+	 const double bq = sgn * bope_c( ( kb - 1 ) + 6 * ( q - 1 ) );
+	 if( !any && bq == 0 ) continue; // uniform
+	 const double uq = F( 0, q, o ), vq = F( 1, q, o ), wq = F( 2, q, o );
+	 rz[0] += mc * uq; rz[1] += mc * vq; rz[2] += lc * wq;
+	 if( bq != 0 )
+	 {
+	    bz[0] += bq * uq; bz[1] += bq * vq; bz[2] += bq * wq;
+	    t[0] += bq * g1[q - 1]; t[1] += bq * g2[q - 1]; t[2] += bq * g3[q - 1];
+	 }
+      }
+      {
+	 const double gh = ghcof_c( kb - 1 );
+	 if( gh != 0 )
+	 {
+	    rz[0] += gh * muq[0] * F( 0, 0, o );
+	    rz[1] += gh * muq[0] * F( 1, 0, o );
+	    rz[2] += gh * l2q[0] * F( 2, 0, o );
+	 }
+      }
+      // ---- exchanged products (first differences carry a factor 12)
+      const double bw12 = 12 * bz[2];
+      {
+	 double* const ex = s_ex + ty * PX + tx + 2;
+	 double* const ey = s_ey + ( ty + 2 ) * TX + tx;
+	 ex[0] = l0 * ( sy * dyv + bw12 );
+	 ex[TY * PX] = m0 * dyu;
+	 ex[2 * TY * PX] = m0 * ( 12 * bz[0] );
+	 ey[0] = m0 * dxv;
+	 ey[PY * TX] = l0 * ( sx * dxu + bw12 );
+	 ey[2 * PY * TX] = m0 * ( 12 * bz[1] );
+      }
+      for( int hh = tid; hh < 4 * TY + 4 * TX; hh += NT )
+      {
+	 int sx_, sy_;
+	 const bool xr = hh < 4 * TY;
+	 if( xr ) { const int hx = hh & 3, row = hh >> 2; sx_ = hx < 2 ? hx : TX + hx; sy_ = row + 2; }
+	 else { const int tt = hh - 4 * TY; const int hy = tt >> 5, col = tt & 31; sy_ = hy < 2 ? hy : TY + hy; sx_ = col + 2; }
+	 const int oo = sy_ * PX + sx_;
+	 const double hm = F( 3, kb, oo ), hl = F( 4, kb, oo );
+	 double hb[3] = { 0, 0, 0 };
+#pragma unroll
+	 for( int q = 1; q <= 8; q++ )
+	 {
+	    const double bq = sgn * bope_c( ( kb - 1 ) + 6 * ( q - 1 ) );
+	    if( bq != 0 )
+	    {
+	       hb[0] += bq * F( 0, q, oo ); hb[1] += bq * F( 1, q, oo ); hb[2] += bq * F( 2, q, oo );
+	    }
+	 }
+	 if( xr )
+	 {
+	    const double hdyv = cf_d0u( F( 1, kb, oo - 2 * PX ), F( 1, kb, oo - PX ), F( 1, kb, oo + PX ), F( 1, kb, oo + 2 * PX ) );
+	    const double hdyu = cf_d0u( F( 0, kb, oo - 2 * PX ), F( 0, kb, oo - PX ), F( 0, kb, oo + PX ), F( 0, kb, oo + 2 * PX ) );
+	    double* const hx_ = s_ex + ( sy_ - 2 ) * PX + sx_;
+	    hx_[0] = hl * ( s_sy[sy_] * hdyv + 12 * hb[2] );
+	    hx_[TY * PX] = hm * hdyu;
+	    hx_[2 * TY * PX] = hm * ( 12 * hb[0] );
+	 }
+	 else
+	 {
+	    const double hdxv = cf_d0u( F( 1, kb, oo - 2 ), F( 1, kb, oo - 1 ), F( 1, kb, oo + 1 ), F( 1, kb, oo + 2 ) );
+	    const double hdxu = cf_d0u( F( 0, kb, oo - 2 ), F( 0, kb, oo - 1 ), F( 0, kb, oo + 1 ), F( 0, kb, oo + 2 ) );
+	    double* const hy_ = s_ey + sy_ * TX + ( sx_ - 2 );
+	    hy_[0] = hm * hdxv;
+	    hy_[PY * TX] = hl * ( s_sx[sx_] * hdxu + 12 * hb[2] );
+	    hy_[2 * PY * TX] = hm * ( 12 * hb[1] );
+	 }
+      }
+      __syncthreads();
+      if( act )
+      {
+	 const double* const ex = s_ex + ty * PX + tx + 2;
+	 const double* const ey = s_ey + ( ty + 2 ) * TX + tx;
+	 const double x1 = cf_d0u( ex[-2], ex[-1], ex[1], ex[2] );
+	 const double x2 = cf_d0u( ex[TY * PX - 2], ex[TY * PX - 1], ex[TY * PX + 1], ex[TY * PX + 2] );
+	 const double x3 = cf_d0u( ex[2 * TY * PX - 2], ex[2 * TY * PX - 1], ex[2 * TY * PX + 1], ex[2 * TY * PX + 2] );
+	 const double y1 = cf_d0u( ey[-2 * TX], ey[-TX], ey[TX], ey[2 * TX] );
+	 const double y2 = cf_d0u( ey[PY * TX - 2 * TX], ey[PY * TX - TX], ey[PY * TX + TX], ey[PY * TX + 2 * TX] );
+	 const double y3 = cf_d0u( ey[2 * PY * TX - 2 * TX], ey[2 * PY * TX - TX], ey[2 * PY * TX + TX], ey[2 * PY * TX + 2 * TX] );
+	 const double i6 = 1.0 / 6, i144 = 1.0 / 144;
+	 double r[3];
+	 r[0] = ( i6 * pr[0] + rz[0] ) + i144 * ( sx * ( x1 + sy * y1 + 12 * t[0] ) );
+	 r[1] = ( i6 * pr[1] + rz[1] ) + i144 * ( sy * ( sx * x2 + y2 + 12 * t[1] ) );
+	 r[2] = ( i6 * pr[2] + rz[2] ) + i144 * ( sx * x3 + sy * y3 + 12 * t[2] );
+	 const int k = side == 0 ? kb : a.nk - kb + 1;
+	 const long long p = (long long)li + (long long)b.ni * lj + b.nij * ( k - b.kfirst );
+	 if( STAGED_OPS )
+	 {
+	    // rhs_epilogue<MODE> with rho, um / up taken from the staged operands and u from the staged plane
+	    const double* const d = s_op + ( kb - 1 ) * 4 * NT + tid;
+	    const double rho = d[0];
+	    const double uk[3] = { u0, v0, w0 };
+	    const double dt2 = a.dt * a.dt;
+	    const double f = MODE == MODE_PRED ? dt2 / rho : ( dt2 * dt2 / 12 ) / rho;
+#pragma unroll
+	    for( int c = 0; c < 3; c++ )
+	    {
+	       const long long q = c * b.sc + b.sp * p;
+	       const double fo = a.fo ? a.fo[q] : 0.0;
+	       const double acc = cof * r[c] + fo;
+	       if( MODE == MODE_PRED )
+	       {
+		  a.out[q] = 2 * uk[c] - d[( c + 1 ) * NT] + f * acc;
+		  if( a.out2 ) a.out2[q] = acc / rho;
+	       }
+	       else
+		  a.out[q] = d[( c + 1 ) * NT] + f * acc;
+	    }
+	 }
+	 else
+	    rhs_epilogue<MODE>( a, p, li + b.ifirst, lj + b.jfirst, k, cof, r );
+      }
+      __syncthreads(); // the exchange buffers are reused by the next row
+   }
+}
+
 // the 2-point shell where L(u) is never written (stays 0 in the reference): pred/corr with lu=0.
 // Enumerates the shell as 6 slabs: k-low, k-high (full planes), j-low, j-high, i-low, i-high.
 template <int MODE>
@@ -695,9 +978,45 @@ static int launch_rows_general( RhsMode mode, const RhsArgs& a, int k_lo, int k_
    return check_launch( "k_rhs_v1" );
 }
 
+// set by api.cu: the runtime tables (sw4b200_copy_stencilcoefficients) equal the built-in ones
+bool g_builtin_sbp_tables = true;
+
+static int closure_generation()
+{
+   if( !g_builtin_sbp_tables ) return 1; // k_closure_fast has the built-in tables folded in at compile time
+   static int v = -1;
+   if( v < 0 )
+   {
+      const char* e = getenv( "SW4B200_CLOSURE_GEN" );
+      v = ( e && e[0] == '1' ) ? 1 : 2;
+   }
+   return v;
+}
+
+template <int MODE>
+static int launch_closure_fast_t( const RhsArgs& a, int side, int kb_lo, int kb_hi, cudaStream_t st )
+{
+   static bool configured = false;
+   const size_t smem = (size_t)CF_SMEM_DOUBLES * sizeof( double );
+   if( !configured )
+   {
+      cudaError_t e = cudaFuncSetAttribute( k_closure_fast<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem );
+      if( e != cudaSuccess ) return set_error( "k_closure_fast: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString( e ) );
+      configured = true;
+   }
+   const Block& b = a.b;
+   ProfScope prof( "closure", st );
+   dim3 bs( CL_TX, CL_TY, 1 );
+   dim3 gs( ( b.ni - 4 + CL_TX - 1 ) / CL_TX, ( b.nj - 4 + CL_TY - 1 ) / CL_TY, 1 );
+   k_closure_fast<MODE><<<gs, bs, smem, st>>>( a, side, kb_lo, kb_hi );
+   count_launch();
+   return check_launch( "k_closure_fast" );
+}
+
 template <int MODE>
 static int launch_closure_t( const RhsArgs& a, int side, int kb_lo, int kb_hi, cudaStream_t st )
 {
+   if( closure_generation() == 2 ) return launch_closure_fast_t<MODE>( a, side, kb_lo, kb_hi, st );
    static bool configured = false;
    const size_t smem = (size_t)5 * CL_NP * CL_PLANE * sizeof( double );
    if( !configured )

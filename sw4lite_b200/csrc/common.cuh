@@ -47,6 +47,8 @@ struct Int6 { int v[6]; };
 struct Int36 { int v[36]; };
 struct Ptr6 { const double* p[6]; };
 
+extern bool g_builtin_sbp_tables; // cart_v1.cu
+
 // error plumbing (api.cu)
 int set_error( const char* fmt, ... );
 int check_launch( const char* what );
