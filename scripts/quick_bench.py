@@ -40,3 +40,18 @@ timeit("rhs4_pred (fused)", lambda: chk(lib.sw4b200_rhs4_pred(1, *box.bounds, n 
 timeit("rhs4_corr (fused, sg4)", lambda: chk(lib.sw4b200_rhs4_corr(1, *box.bounds, n - 4, os_, p(out), p(up), p(u), p(um), p(mu), p(la), p(rho), None, p(sx), p(sy), p(sz), p(dc[0]), p(dc[1]), p(dc[2]), p(co[0]), p(co[1]), p(co[2]), 0.02, 4, 0.1, 0.01, sp)), 120)
 timeit("rhs4_corr (fused, no sg)", lambda: chk(lib.sw4b200_rhs4_corr(1, *box.bounds, n - 4, os_, p(out), p(up), p(u), p(um), p(mu), p(la), p(rho), None, p(sx), p(sy), p(sz), p(dc[0]), p(dc[1]), p(dc[2]), p(co[0]), p(co[1]), p(co[2]), 0.0, 0, 0.1, 0.01, sp)), 120)
 print("launches", lib.sw4b200_kernel_launch_count())
+
+# curvilinear operator (general kernel)
+if len(sys.argv) > 2:
+    nc = int(sys.argv[2])
+    cb = Box(nc, nc, nc // 2)
+    cn = cb.npts
+    cu, clu = t(3 * cn), t(3 * cn)
+    cmu, cla, cjac = t(cn), t(cn), t(cn)
+    cmet = t(4 * cn)
+    csx, csy = t(nc), t(nc)
+    cint = (nc - 4) ** 2 * (nc // 2 - 4)
+    interior = cint
+    for top in (0, 1):
+        os2 = ints((0, 0, 0, 0, top, 0))
+        timeit("rhs4sgcurv (top=%d)" % top, lambda: chk(lib.sw4b200_rhs4sgcurv(1, *cb.bounds, p(cu), p(cmu), p(cla), p(cmet), p(cjac), p(clu), os2, p(csx), p(csy), sp)), 104)

@@ -73,21 +73,40 @@ class HaloExchange:
 
 class SlabStepper:
     """one time step of a z-slab (EW.C:2527-2842 with the halo swap on k): face rows -> exchange
-    (overlapped with the bulk rows) -> boundary conditions, twice per step."""
+    (overlapped with the bulk rows) -> boundary conditions, twice per step.
 
-    def __init__(self, blk, exchange):
-        self.blk, self.ex = blk, exchange
+    `curv`: the curvilinear block under the topography (config 4), held whole by the rank that owns the top
+    Cartesian slab (rank 0): it steps between the face rows and the bulk rows of the Cartesian slab, so its
+    work also overlaps the halo transfer, and is coupled to the Cartesian slab by EW::enforceCartTopo
+    (EW.C:3504-3531) after the boundary conditions, as in EW::enforceBC (EW.C:3500)."""
 
-    def step(self, f=None, ftt=None):
+    def __init__(self, blk, exchange, curv=None):
+        self.blk, self.ex, self.curv = blk, exchange, curv
+
+    def _bc(self):
+        b = self.blk
+        b.enforce_bc()
+        if self.curv is not None:
+            from . import lib as L
+            self.curv.enforce_bc()
+            L.check(b.lib.sw4b200_grid_enforce_cart_topo(b.h, self.curv.h))
+
+    def step(self, f=None, ftt=None, fcurv=None, fttcurv=None):
         b = self.blk
         b.predictor_part(1, f)
         b.begin_exchange(self.ex, with_acc=True)    # Up and the stored acceleration of the face planes
+        if self.curv is not None:
+            self.curv.predictor(fcurv)
         b.predictor_part(2, f)
         b.end_exchange(self.ex, with_acc=True)
-        b.enforce_bc()
+        self._bc()
         b.corrector_part(1, ftt)
         b.begin_exchange(self.ex)
+        if self.curv is not None:
+            self.curv.corrector(fttcurv)
         b.corrector_part(2, ftt)
         b.end_exchange(self.ex)
-        b.enforce_bc()
+        self._bc()
         b.cycle()
+        if self.curv is not None:
+            self.curv.cycle()
