@@ -156,6 +156,14 @@ int sw4b200_rhs4_corr( int corder, int ifirst, int ilast, int jfirst, int jlast,
                        const double* d_cox, const double* d_coy, const double* d_coz,
                        double beta, int sg_order, double h, double dt, void* stream );
 
+/* replaces rhs4_corr_gpu (device-routines.h:297) as the reference's time loop calls it (RHSCorrCU_center, EW_cuda.C:1325):
+ * the corrector with the acceleration already formed by evalDpDmInTimeCU, in place on up:
+ *   up += dt^4/(12 rho) * ( L(uacc)/h^2 + fo )              d_fo may be NULL */
+int sw4b200_rhs4_corr_acc( int corder, int ifirst, int ilast, int jfirst, int jlast, int kfirst, int klast,
+                           int nk, const int* h_onesided, double* d_up, const double* d_uacc, const double* d_mu,
+                           const double* d_lambda, const double* d_rho, const double* d_fo, const double* d_strx,
+                           const double* d_stry, const double* d_strz, double h, double dt, void* stream );
+
 /* ---------------------------------------------------------------- sparse forcing / receivers
  * replaces EW::ForceCU (EW_cuda.C:709) + forcing_dev (device-routines.C:8306): adds
  * factor/rho(p) * f to up at n unique source points; d_pidx = flat point index (i-fastest),

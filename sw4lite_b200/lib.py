@@ -59,6 +59,7 @@ SIGNATURES = {
     "sw4b200_enforce_cart_topo": (I, [I, VP] + B6 + [VP, I, I, VP]),
     "sw4b200_rhs4_pred": (I, [I] + B6 + [I, c_ip] + [VP] * 10 + [D, D, VP]),
     "sw4b200_rhs4_corr": (I, [I] + B6 + [I, c_ip] + [VP] * 17 + [D, I, D, D, VP]),
+    "sw4b200_rhs4_corr_acc": (I, [I] + B6 + [I, c_ip] + [VP] * 9 + [D, D, VP]),
     "sw4b200_add_point_forces": (I, [I, C.c_size_t, VP, VP, I, VP, VP, D, VP]),
     "sw4b200_gather_points": (I, [I, C.c_size_t, VP, I, VP, VP, VP]),
     "sw4b200_rhs4sg_host": (I, [I] + B6 + [I, c_ip] + [c_dp] * 4 + [D] + [c_dp] * 3),
