@@ -2,6 +2,7 @@
 #include "cart_v1.cu"
 #include "rhs4sg_fast.cu"
 #include "rhs4sg_fast2.cu"
+#include "rhs4sg_fast3.cu"
 #include "addsgd_fast.cu"
 #include "curvilinear.cu"
 #include "api.cu"

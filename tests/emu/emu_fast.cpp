@@ -9,8 +9,21 @@ std::barrier<>* g_barrier = 0;
 }
 #include "../../sw4lite_b200/csrc/rhs4sg_fast.cu"
 #include "../../sw4lite_b200/csrc/rhs4sg_fast2.cu"
+#include "../../sw4lite_b200/csrc/rhs4sg_fast3.cu"
 
 using namespace sw4b200;
+
+// third generation: gen = 3000 + 10*TY + TMODE
+template <int TY, int TMODE>
+static void run_fast3( int epi, const FastArgs& a )
+{
+   typedef fast3::Cfg<TY> C3;
+   dim3 bs( C3::TX, TY, 1 );
+   dim3 gs( ( a.b.ni - 4 + C3::TX - 1 ) / C3::TX, ( a.b.nj - 4 + TY - 1 ) / TY, ( a.khi - a.klo + 1 + a.kchunk - 1 ) / a.kchunk );
+   if( epi == EPI_LU ) emu::launch( gs, bs, C3::SMEM_DOUBLES, [&]() { k_rhs_fast3<TY, EPI_LU, TMODE>( a ); } );
+   else if( epi == EPI_PRED ) emu::launch( gs, bs, C3::SMEM_DOUBLES, [&]() { k_rhs_fast3<TY, EPI_PRED, TMODE>( a ); } );
+   else emu::launch( gs, bs, C3::SMEM_DOUBLES, [&]() { k_rhs_fast3<TY, EPI_CORR, TMODE>( a ); } );
+}
 
 extern "C" int emu_rhs_fast( int gen, int epi, int ifirst, int ilast, int jfirst, int jlast, int kfirst, int klast, int klo, int khi,
 			     int kchunk, const double* u, const double* mu, const double* la, const double* strx,
@@ -30,6 +43,17 @@ extern "C" int emu_rhs_fast( int gen, int epi, int ifirst, int ilast, int jfirst
       a.fo[c] = fo ? fo + c * n : 0;
    }
    a.mu = mu; a.la = la; a.strx = strx; a.stry = stry; a.strz = strz; a.cof6 = cof / 6; a.cof144 = cof / 144; a.rho = rho; a.fac = fac;
+   if( gen >= 3000 )
+   {
+      switch( gen - 3000 )
+      {
+      case 81: run_fast3<8, 1>( epi, a ); break;
+      case 82: run_fast3<8, 2>( epi, a ); break;
+      case 121: run_fast3<12, 1>( epi, a ); break;
+      default: run_fast3<12, 2>( epi, a ); break;
+      }
+      return 0;
+   }
    constexpr int TY = 8;
    typedef fast::Cfg<TY> C;
    dim3 bs( C::TX, TY, 1 );

@@ -17,9 +17,19 @@ LIB = os.path.join(EMU, "libemu_fast.so")
 SRC = [os.path.join(EMU, "emu_fast.cpp"), os.path.join(EMU, "cuda_emu.h"),
        os.path.join(HERE, "..", "sw4lite_b200", "csrc", "rhs4sg_fast.cu"),
        os.path.join(HERE, "..", "sw4lite_b200", "csrc", "rhs4sg_fast2.cu"),
+       os.path.join(HERE, "..", "sw4lite_b200", "csrc", "rhs4sg_fast3.cu"),
        os.path.join(HERE, "..", "sw4lite_b200", "csrc", "common.cuh")]
 _dp = C.POINTER(C.c_double)
-GEN = 2  # generation of the fast kernel under test (rhs4sg_fast2.cu is the product path)
+GEN = 2  # generation of the fast kernel under test, set per test by the fixture below
+
+
+@pytest.fixture(autouse=True, params=[2, 3122, 3121, 3082], ids=["fast2", "fast3-12w-tm2", "fast3-12w-tm1", "fast3-8w-tm2"])
+def generation(request):
+    """2: rhs4sg_fast2.cu; 3000+10*TY+TMODE: rhs4sg_fast3.cu (the product path is 3122: 32x12 tile, z delay lines
+    and g rings in tensor memory -- emulated here as a per-thread array)"""
+    global GEN
+    GEN = request.param
+    yield
 
 
 @pytest.fixture(scope="module")
