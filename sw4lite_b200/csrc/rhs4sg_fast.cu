@@ -446,6 +446,7 @@ int fast_kchunk( const Block& b, int nplanes, int ty )
 
 int launch_fast2( int epi, FastArgs a, cudaStream_t st );
 int launch_fast3( int variant, int epi, const FastArgs& a, cudaStream_t st );
+int launch_fast4( int epi, const FastArgs& a, cudaStream_t st );
 
 // Generation of the interior kernel.  Default: the third generation (rhs4sg_fast3.cu, 32x12 tile, z state in
 // tensor memory).  SW4B200_FAST_GEN=1 / 2 select the earlier generations, 3000+10*TY+TMODE a variant of the third
@@ -458,7 +459,7 @@ static int fast_generation()
       const char* e = getenv( "SW4B200_FAST_GEN" );
       v = e ? atoi( e ) : SW4B200_DEFAULT_FAST_GEN;
       if( v == 3 ) v = 3122;
-      if( v != 1 && v != 2 && v != 3122 && v != 3121 && v != 3082 && v != 3081 ) v = SW4B200_DEFAULT_FAST_GEN;
+      if( v != 1 && v != 2 && v != 4 && v != 3122 && v != 3121 && v != 3082 && v != 3081 ) v = SW4B200_DEFAULT_FAST_GEN;
    }
    return v;
 }
@@ -466,6 +467,7 @@ static int fast_generation()
 int launch_fast( int epi, FastArgs a, cudaStream_t st )
 {
    if( a.khi < a.klo ) return 0;
+   if( fast_generation() == 4 ) return launch_fast4( epi, a, st );
    if( fast_generation() >= 3000 ) return launch_fast3( fast_generation() - 3000, epi, a, st );
    if( fast_generation() == 2 ) return launch_fast2( epi, a, st );
    if( a.kchunk <= 0 ) a.kchunk = fast_kchunk( a.b, a.khi - a.klo + 1, 8 );

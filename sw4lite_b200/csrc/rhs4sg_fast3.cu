@@ -61,9 +61,9 @@ struct Tm
 {
    double mem[256];
    template <int COL, int N> // N doubles to columns COL..COL+2N-1
-   __device__ __forceinline__ void st( const double* v ) { for( int i = 0; i < N; i++ ) mem[COL / 2 + i] = v[i]; }
+   __device__ __forceinline__ void st( const double* v, int off = 0 ) { for( int i = 0; i < N; i++ ) mem[( COL + off ) / 2 + i] = v[i]; }
    template <int COL, int N>
-   __device__ __forceinline__ void ld( TmVal* r ) const { for( int i = 0; i < N; i++ ) r[i].v = mem[COL / 2 + i]; }
+   __device__ __forceinline__ void ld( TmVal* r, int off = 0 ) const { for( int i = 0; i < N; i++ ) r[i].v = mem[( COL + off ) / 2 + i]; }
    __device__ __forceinline__ void wait_st() const {}
    template <int N>
    __device__ __forceinline__ void wait_ld( TmVal* ) const {}
@@ -77,10 +77,10 @@ struct Tm
 {
    uint32_t base; // tensor-memory address of the strip: (first lane of the warp's quadrant) << 16 | first column
    template <int COL, int N>
-   __device__ __forceinline__ void st( const double* v )
+   __device__ __forceinline__ void st( const double* v, int off = 0 ) // off: run-time column offset (warp uniform)
    {
       static_assert( N == 1 || N == 2 || N == 4 || N == 8, "st: 1, 2, 4 or 8 doubles" );
-      const uint32_t ta = base + COL;
+      const uint32_t ta = base + COL + off;
       if constexpr( N == 1 )
 	 asm volatile( "tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"( ta ), SW4_LO( v[0] ), SW4_HI( v[0] ) : "memory" );
       else if constexpr( N == 2 )
@@ -99,10 +99,10 @@ struct Tm
 		       : "memory" );
    }
    template <int COL, int N>
-   __device__ __forceinline__ void ld( TmVal* r ) const
+   __device__ __forceinline__ void ld( TmVal* r, int off = 0 ) const
    {
       static_assert( N == 1 || N == 2 || N == 4 || N == 8, "ld: 1, 2, 4 or 8 doubles" );
-      const uint32_t ta = base + COL;
+      const uint32_t ta = base + COL + off;
       if constexpr( N == 1 )
 	 asm volatile( "tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"( r[0].lo ), "=r"( r[0].hi ) : "r"( ta ) );
       else if constexpr( N == 2 )

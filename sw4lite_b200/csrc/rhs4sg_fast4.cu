@@ -1,0 +1,707 @@
+// Throughput path for the Cartesian interior rows, fourth generation (SoA layout, corder=1):
+// register blocking over x-pairs with the z state of both points in tensor memory.
+//
+// Same operator algebra and one-barrier-per-plane z-march as rhs4sg_fast2.cu / rhs4sg_fast3.cu (reference formulas
+// rhs4sg_rev.C:112-348 with the common subexpressions shared between threads).  ncu on those kernels
+// (profiles/r01c_fast3_ncu.md) showed a kernel that waits: issue slots 43 %, fp64 pipe 40 %, shared-memory pipe 67 %,
+// 8 warps per SM; a third of the instructions were integer/address work, and 12 warps only moved the stall to the
+// memory-instruction queue.  The cure for a latency-bound stencil is more independent work per thread and fewer
+// memory instructions per point, i.e. register blocking -- which the z rings and delay lines (70 doubles per point)
+// made impossible.  With those in tensor memory (rhs4sg_fast3.cu) it fits:
+//   * every thread owns TWO x-adjacent points of a 32x16 tile (256 threads, 16 pairs per row, 2 rows per warp);
+//   * every shared-memory access is a 16-byte LDS.128/STS.128 on an aligned pair: the six x values i-2..i+3 of a field
+//     serve both points (3 loads instead of 10), y neighbours and the exchanged cross products come as pairs;
+//     62 shared-memory instructions per pair and plane instead of 2 x 103;
+//   * x-direction coefficient products (mu sx, (2mu+la) sx at i-2..i+3) are shared by the pair;
+//   * per plane and point 10 doubles go to tensor memory (tcgen05.st) when plane p arrives and come back
+//     (tcgen05.ld) when plane p-2 is finished: g1,g2,g3 (read at p+1,p+3,p+4), the in-plane sums pr[3] and the
+//     in-plane parts of the exchanged products la sy D0y v, mu D0y u, mu D0x v, la sx D0x u.  Registers keep only
+//     the five-plane rings of u,v,w, mu sz, (2mu+la) sz of the two points;
+//   * mu and la are needed in shared memory only for the plane that arrives (2 slots instead of 6; the ring points
+//     of the tile keep a 3-deep side copy), which is what lets a 32x16 tile fit in 227 KB.
+// sz is folded into the z-type exchanged products (E3 = mu sz D0z u, E6 = mu sz D0z v) and la sz = (2mu+la)sz - 2 mu sz
+// comes from the register rings, so mu, la themselves need no delay line.
+//
+// Tensor-memory layout: 8 warps, warp w owns lanes 32 (w%4)..+31 and columns 256 (w/4)..+255; a thread's record of
+// plane p sits in ring slot p mod 6, 40 columns (A,B = the two points):
+//    0-11 g1A g1B g2A g2B g3A g3B | 12-39 pr0A pr0B pr1A pr1B pr2A pr2B e1A e1B e2A e2B e4A e4B e5A e5B
+//
+// Also compiled by g++ (SW4B200_EMULATE) for the CPU check of the kernel source (tests/emu).
+#include "common.cuh"
+
+namespace sw4b200 {
+
+namespace fast4 {
+
+using fast::W4;
+using fast::weights4;
+using fast::gsum;
+using fast::d0u;
+using fast3::Tm;
+using fast3::TmVal;
+using fast3::tm_get;
+
+#if defined( SW4B200_EMULATE )
+struct D2 { double x, y; };
+#else
+typedef double2 D2;
+#endif
+__device__ __forceinline__ D2 ld2( const double* p ) { return *reinterpret_cast<const D2*>( p ); }
+__device__ __forceinline__ void st2( double* p, double x, double y )
+{
+   D2 v;
+   v.x = x; v.y = y;
+   *reinterpret_cast<D2*>( p ) = v;
+}
+
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: rows of a plane go from global to
+// shared memory without passing through registers, the LSU queue or per-thread address arithmetic
+#if defined( SW4B200_EMULATE )
+__device__ __forceinline__ void mbar_init( double*, int ) {}
+__device__ __forceinline__ void mbar_arrive_expect( double*, int ) {}
+__device__ __forceinline__ void mbar_wait( double*, int ) {}
+__device__ __forceinline__ void bulk_copy( double* dst, const double* src, int bytes, double* )
+{
+   for( int i = 0; i < bytes / 8; i++ ) dst[i] = src[i];
+}
+#else
+__device__ __forceinline__ void mbar_init( double* mbar, int count )
+{
+   asm volatile( "mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"( (uint32_t)__cvta_generic_to_shared( mbar ) ), "r"( count ) : "memory" );
+}
+__device__ __forceinline__ void mbar_arrive_expect( double* mbar, int bytes )
+{
+   asm volatile( "mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"( (uint32_t)__cvta_generic_to_shared( mbar ) ), "r"( bytes )
+		 : "memory" );
+}
+__device__ __forceinline__ void mbar_wait( double* mbar, int parity )
+{
+   asm volatile( "{\n\t"
+		 ".reg .pred P1;\n\t"
+		 "SW4_MBAR_WAIT:\n\t"
+		 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+		 "@P1 bra SW4_MBAR_DONE;\n\t"
+		 "bra SW4_MBAR_WAIT;\n\t"
+		 "SW4_MBAR_DONE:\n\t"
+		 "}" ::"r"( (uint32_t)__cvta_generic_to_shared( mbar ) ),
+		 "r"( parity )
+		 : "memory" );
+}
+// bytes: multiple of 16; dst, src 16-byte aligned
+__device__ __forceinline__ void bulk_copy( double* dst, const double* src, int bytes, double* mbar )
+{
+   asm volatile( "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+		     (uint32_t)__cvta_generic_to_shared( dst ) ),
+		 "l"( src ), "r"( bytes ), "r"( (uint32_t)__cvta_generic_to_shared( mbar ) )
+		 : "memory" );
+}
+#endif
+
+template <int TY>
+struct Cfg
+{
+   static constexpr int TXP = 16, TX = 2 * TXP, PX = TX + 4, PY = TY + 4, PLANE = PX * PY, NT = TXP * TY, NSLOT = 6;
+   static constexpr int NH = 4 * TY + 4 * TX; // ring points of the tile per plane
+   static constexpr int NCP_PLANE = 5 * PY, NCP_OPS = 4 * TY; // row copies per plane: u,v,w,mu,la rows ; rho,um rows
+   static constexpr int EX = 3 * TY * PX, EY = 3 * PY * TX;
+   static constexpr int OPS = 4 * TX * TY; // epilogue operands of one plane: rho, um[3] of the own points
+   static constexpr int SZMAX = 512;	   // strz of the planes a CTA marches through (kchunk + 6 <= SZMAX)
+   // shared memory, in doubles (every region starts on a 16-byte boundary)
+   static constexpr int O_UVW = 0;			      // [3][NSLOT][PLANE]
+   static constexpr int O_ML = O_UVW + 3 * NSLOT * PLANE;     // [2][2][PLANE]   mu, la of the arriving plane
+   static constexpr int O_EX = O_ML + 4 * PLANE;	      // [2][3][TY][PX]  E1..E3, double buffered
+   static constexpr int O_EY = O_EX + 2 * EX;		      // [2][3][PY][TX]  E4..E6
+   static constexpr int O_HML = O_EY + 2 * EY;		      // [3][2][NH]      mu, la of the ring points, planes p-2..p
+   static constexpr int O_SX = O_HML + 6 * NH;		      // [PX]
+   static constexpr int O_SY = O_SX + PX;		      // [PY]
+   static constexpr int O_OP = O_SY + PY;		      // [2][4][TX*TY]
+   static constexpr int O_SZ = O_OP + 2 * OPS;		      // [SZMAX]
+   static constexpr int O_MBAR = O_SZ + SZMAX;		      // two mbarriers (even / odd planes)
+   static constexpr int SMEM_DOUBLES = O_MBAR + 2 + 2;	      // + the tensor-memory base address
+   static_assert( NCP_PLANE + NCP_OPS <= NT, "one row copy per thread" );
+   static constexpr int REC = 40;			      // tensor-memory columns per plane record
+   static constexpr int COLS = 256;			      // columns per warp of a lane quadrant (8 warps)
+   static_assert( NT == 256, "8 warps: two per tensor-memory lane quadrant" );
+   static_assert( NSLOT * REC <= COLS, "tensor-memory strip too small" );
+   static_assert( ( PLANE % 2 ) == 0 && ( EX % 2 ) == 0 && ( EY % 2 ) == 0 && ( NH % 2 ) == 0 && ( ( PX + PY ) % 2 ) == 0, "16-byte alignment" );
+};
+
+// per-thread register state ([..][2]: the two points): five-plane shift registers, [4] = plane p ... [0] = plane p-4.
+// The march is ONE step body executed for every plane (the rings of the earlier generations needed a step copy per
+// ring position, 6 x 1600 instructions: more than the instruction cache holds); the 40 register moves per step
+// go to the integer pipes, which idle next to the fp64 pipe.
+struct State
+{
+   double cu[5][2], cv[5][2], cw[5][2], amz[5][2], alz[5][2];
+   double rp[3][2]; // result of the previous plane, still lacking the exchanged cross terms
+};
+
+template <int TY>
+struct Ctx
+{
+   typedef Cfg<TY> C;
+   double* sm;
+   int p0;
+   int li0, lj0; // local (array) index of the tile's first output
+   int tid, txh, ty, o;
+   int ka, kb, pend;
+   bool act[2];
+   long long gown; // offset of the left point inside a plane
+};
+
+// run-time (CTA-uniform) offsets of one step: [j] = plane p-j
+struct Ph
+{
+   int slot;   // p mod 6
+   int o[5];   // PLANE * slot of plane p-j in the u,v,w ring
+   int c[5];   // REC * slot: tensor-memory column of the record of plane p-j
+   int par;    // p & 1: E buffer written, mu/la slot, operand buffer
+   int wpar;   // bit b: phase parity to wait for on mbarrier b
+   int t0, t2; // 2 NH (p mod 3), 2 NH ((p-2) mod 3): side copies of the ring points' mu, la
+};
+
+// stage plane p: every thread below NCP issues ONE row copy (TMA bulk copy, completing on the mbarrier of the plane's
+// parity): rows of u,v,w into ring slot `slot`, rows of mu,la into slot `par`; with an epilogue also the own-row
+// operands (rho, um) of plane p-3, the plane that the step handling plane p finishes, into operand buffer `par`.
+// Requires 16-byte aligned rows: ni even, array bases 16-byte aligned (launch_fast4 checks; other grids take the
+// cp.async kernel rhs4sg_fast2.cu).  Out-of-array parts of the tile are not filled: only points outside the
+// interior ever read them, and those are never stored.
+template <int TY, int EPI>
+__device__ __forceinline__ void stage( const FastArgs& a, const Ctx<TY>& c, int p, int slot, int par )
+{
+   typedef Cfg<TY> C;
+   constexpr int NCP = C::NCP_PLANE + ( EPI != EPI_LU ? C::NCP_OPS : 0 );
+   if( p > c.pend + 1 || c.tid >= NCP ) return;
+   const Block& b = a.b;
+   double* const mbar = c.sm + C::O_MBAR + par;
+   const double* src = 0;
+   double* dst = 0;
+   int n = 0; // doubles
+   if( c.tid < C::NCP_PLANE )
+   {
+      const int f = c.tid / C::PY, row = c.tid - f * C::PY;
+      const int lj = c.lj0 - 2 + row, li = c.li0 - 2;
+      if( p <= c.pend && lj < b.nj ) // (the step after the last plane only finishes plane kb)
+      {
+	 n = b.ni - li < C::PX ? b.ni - li : C::PX;
+	 const long long g = b.nij * ( p - b.kfirst ) + (long long)lj * b.ni + li;
+	 src = ( f == 0 ? a.u[0] : f == 1 ? a.u[1] : f == 2 ? a.u[2] : f == 3 ? a.mu : a.la ) + g;
+	 dst = c.sm + ( f < 3 ? C::O_UVW + ( f * C::NSLOT + slot ) * C::PLANE : C::O_ML + ( ( f - 3 ) * 2 + par ) * C::PLANE ) + row * C::PX;
+      }
+   }
+   else if( EPI != EPI_LU )
+   {
+      const int t = c.tid - C::NCP_PLANE;
+      const int f = t / TY, row = t - f * TY;
+      const int lj = c.lj0 + row, kq = p - 3;
+      if( kq >= c.ka && kq <= c.kb && lj < b.nj && c.li0 < b.ni )
+      {
+	 n = b.ni - c.li0 < C::TX ? b.ni - c.li0 : C::TX;
+	 const long long g = b.nij * ( kq - b.kfirst ) + (long long)lj * b.ni + c.li0;
+	 src = ( f == 0 ? a.rho : a.um[f - 1] ) + g;
+	 dst = c.sm + C::O_OP + par * C::OPS + f * C::TX * TY + row * C::TX;
+      }
+   }
+   mbar_arrive_expect( mbar, 8 * n );
+   if( n > 0 ) bulk_copy( dst, src, 8 * n, mbar );
+}
+
+__device__ __forceinline__ double pick( const D2& v, int t ) { return t ? v.y : v.x; }
+
+// One step of the march: plane p has been staged into ring slot S.  Does the in-plane work of plane p,
+// the z work of plane k=p-2 (publishing its exchanged products in E buffer S&1) and finishes plane k-1
+// (reading E buffer (S+1)&1).
+template <int TY, int EPI>
+__device__ __forceinline__ void step( const FastArgs& a, Ctx<TY>& c, State& s, Tm& tm, const int p, const Ph& ph )
+{
+   typedef Cfg<TY> C;
+   constexpr int TX = C::TX, PX = C::PX, PY = C::PY, PLANE = C::PLANE, NT = C::NT, NSLOT = C::NSLOT, NH = C::NH;
+   // shift-register positions of planes p, p-1, ..., p-4
+   constexpr int R0 = 4, R1 = 3, R2 = 2, R3 = 1, R4 = 0;
+   const int EB = ph.par, EF = ph.par ^ 1, ML = ph.par;
+   const Block& b = a.b;
+   const int k = p - 2, kf = p - 3;
+
+   mbar_wait( c.sm + C::O_MBAR + ph.par, ( ph.wpar >> ph.par ) & 1 ); // the rows of plane p have landed
+   __syncthreads(); // the E products of plane k-1 are visible; slot of plane p-5 is free
+   stage<TY, EPI>( a, c, p + 1, ph.slot == NSLOT - 1 ? 0 : ph.slot + 1, ph.par ^ 1 );
+   tm.wait_st(); // the records stored by the earlier steps (long done) are readable
+
+   const bool kfin = kf >= c.ka && kf <= c.kb;
+   const bool fin[2] = { c.act[0] && kfin, c.act[1] && kfin };
+   const long long qf = kfin ? b.nij * ( kf - b.kfirst ) + c.gown : 0;
+
+   // strx at i-2..i+3 (i = left point), stry at j-2..j+2: re-read every step instead of held in 22 registers
+   double csx[6], csy[5];
+   {
+      const D2 s0 = ld2( c.sm + C::O_SX + 2 * c.txh ), s1 = ld2( c.sm + C::O_SX + 2 * c.txh + 2 ), s2 = ld2( c.sm + C::O_SX + 2 * c.txh + 4 );
+      csx[0] = s0.x; csx[1] = s0.y; csx[2] = s1.x; csx[3] = s1.y; csx[4] = s2.x; csx[5] = s2.y;
+#pragma unroll
+      for( int j = 0; j < 5; j++ ) csy[j] = c.sm[C::O_SY + c.ty + j];
+   }
+   const double syo = csy[2];
+   const double sxo[2] = { csx[2], csx[3] };
+   double g1n[2], g2n[2], g3n[2]; // g products of plane p
+   // ---- in-plane pieces of plane p: an x pass and a y pass over the fields, so that only the weights of one
+   // direction (2 points x 2 coefficient sets) are live next to the neighbours of one field
+   {
+      double* const sm = c.sm;
+      const double* const pf[3] = { sm + C::O_UVW + 0 * NSLOT * PLANE + ph.o[0] + c.o, sm + C::O_UVW + 1 * NSLOT * PLANE + ph.o[0] + c.o,
+				    sm + C::O_UVW + 2 * NSLOT * PLANE + ph.o[0] + c.o };
+      const double* const pm = sm + C::O_ML + ( 0 * 2 + ML ) * PLANE + c.o;
+      const double* const pl = sm + C::O_ML + ( 1 * 2 + ML ) * PLANE + c.o;
+      const double szp = sm[C::O_SZ + p - c.p0];
+      double rec[14]; // pr0A pr0B pr1A pr1B pr2A pr2B e1A e1B e2A e2B e4A e4B e5A e5B
+      double m0[2], l0[2], q0[3][2], dx[3][2], dy[3][2];
+      {
+	 // x-direction coefficients mu sx, (2mu+la) sx at i-2..i+3, shared by the two points
+	 double axm[6], axl[6];
+	 {
+	    const D2 ma = ld2( pm - 2 ), mb = ld2( pm ), mc = ld2( pm + 2 ), la = ld2( pl - 2 ), lb = ld2( pl ), lc = ld2( pl + 2 );
+	    m0[0] = mb.x; m0[1] = mb.y; l0[0] = lb.x; l0[1] = lb.y;
+	    axm[0] = ma.x * csx[0]; axm[1] = ma.y * csx[1]; axm[2] = mb.x * csx[2]; axm[3] = mb.y * csx[3]; axm[4] = mc.x * csx[4]; axm[5] = mc.y * csx[5];
+	    axl[0] = ( 2 * ma.x + la.x ) * csx[0]; axl[1] = ( 2 * ma.y + la.y ) * csx[1]; axl[2] = ( 2 * mb.x + lb.x ) * csx[2];
+	    axl[3] = ( 2 * mb.y + lb.y ) * csx[3]; axl[4] = ( 2 * mc.x + lc.x ) * csx[4]; axl[5] = ( 2 * mc.y + lc.y ) * csx[5];
+	 }
+	 W4 wmx[2], wlx[2];
+#pragma unroll
+	 for( int t = 0; t < 2; t++ )
+	 {
+	    wmx[t] = weights4( axm[t], axm[t + 1], axm[t + 2], axm[t + 3], axm[t + 4] );
+	    wlx[t] = weights4( axl[t], axl[t + 1], axl[t + 2], axl[t + 3], axl[t + 4] );
+	 }
+#pragma unroll
+	 for( int f = 0; f < 3; f++ )
+	 {
+	    const D2 xa = ld2( pf[f] - 2 ), xb = ld2( pf[f] ), xc = ld2( pf[f] + 2 );
+	    const double x[6] = { xa.x, xa.y, xb.x, xb.y, xc.x, xc.y };
+#pragma unroll
+	    for( int t = 0; t < 2; t++ )
+	    {
+	       q0[f][t] = x[2 + t];
+	       dx[f][t] = d0u( x[t], x[t + 1], x[t + 3], x[t + 4] );
+	       rec[2 * f + t] = sxo[t] * gsum( f == 0 ? wlx[t] : wmx[t], x[t], x[t + 1], x[2 + t], x[t + 3], x[t + 4] );
+	    }
+	 }
+      }
+#pragma unroll
+      for( int t = 0; t < 2; t++ )
+      {
+#pragma unroll
+	 for( int j = 0; j < 4; j++ )
+	 {
+	    s.cu[j][t] = s.cu[j + 1][t]; s.cv[j][t] = s.cv[j + 1][t]; s.cw[j][t] = s.cw[j + 1][t];
+	    s.amz[j][t] = s.amz[j + 1][t]; s.alz[j][t] = s.alz[j + 1][t];
+	 }
+	 s.cu[R0][t] = q0[0][t]; s.cv[R0][t] = q0[1][t]; s.cw[R0][t] = q0[2][t];
+	 s.amz[R0][t] = m0[t] * szp; s.alz[R0][t] = ( 2 * m0[t] + l0[t] ) * szp;
+      }
+      {
+	 W4 wmy[2], wly[2];
+	 {
+	    const D2 ma = ld2( pm - 2 * PX ), mb = ld2( pm - PX ), mc = ld2( pm + PX ), md = ld2( pm + 2 * PX );
+	    const D2 la = ld2( pl - 2 * PX ), lb = ld2( pl - PX ), lc = ld2( pl + PX ), ld = ld2( pl + 2 * PX );
+#pragma unroll
+	    for( int t = 0; t < 2; t++ )
+	    {
+	       const double mym2 = pick( ma, t ), mym1 = pick( mb, t ), myp1 = pick( mc, t ), myp2 = pick( md, t );
+	       const double lym2 = pick( la, t ), lym1 = pick( lb, t ), lyp1 = pick( lc, t ), lyp2 = pick( ld, t );
+	       wmy[t] = weights4( mym2 * csy[0], mym1 * csy[1], m0[t] * syo, myp1 * csy[3], myp2 * csy[4] );
+	       wly[t] = weights4( ( 2 * mym2 + lym2 ) * csy[0], ( 2 * mym1 + lym1 ) * csy[1], ( 2 * m0[t] + l0[t] ) * syo,
+				  ( 2 * myp1 + lyp1 ) * csy[3], ( 2 * myp2 + lyp2 ) * csy[4] );
+	    }
+	 }
+#pragma unroll
+	 for( int f = 0; f < 3; f++ )
+	 {
+	    const D2 ya = ld2( pf[f] - 2 * PX ), yb = ld2( pf[f] - PX ), yc = ld2( pf[f] + PX ), yd = ld2( pf[f] + 2 * PX );
+#pragma unroll
+	    for( int t = 0; t < 2; t++ )
+	    {
+	       const double ym2 = pick( ya, t ), ym1 = pick( yb, t ), yp1 = pick( yc, t ), yp2 = pick( yd, t );
+	       dy[f][t] = d0u( ym2, ym1, yp1, yp2 );
+	       rec[2 * f + t] += syo * gsum( f == 1 ? wly[t] : wmy[t], ym2, ym1, q0[f][t], yp1, yp2 );
+	    }
+	 }
+      }
+#pragma unroll
+      for( int t = 0; t < 2; t++ )
+      {
+	 const double e1p = ( l0[t] * syo ) * dy[1][t];	   // la sy D0y v   (in-plane part of E1)
+	 const double e5p = ( l0[t] * sxo[t] ) * dx[0][t]; // la sx D0x u   (in-plane part of E5)
+	 g1n[t] = m0[t] * dx[2][t];
+	 g2n[t] = m0[t] * dy[2][t];
+	 g3n[t] = e1p + e5p;
+	 rec[6 + t] = e1p;
+	 rec[8 + t] = m0[t] * dy[0][t];	 // E2 = mu D0y u
+	 rec[10 + t] = m0[t] * dx[1][t]; // E4 = mu D0x v
+	 rec[12 + t] = e5p;
+      }
+      const double rg[8] = { g1n[0], g1n[1], g2n[0], g2n[1], g3n[0], g3n[1], rec[0], rec[1] };
+      tm.template st<0, 8>( rg, ph.c[0] );	    // cols 0-15
+      tm.template st<16, 8>( rec + 2, ph.c[0] ); // cols 16-31
+      tm.template st<32, 4>( rec + 10, ph.c[0] ); // cols 32-39
+   }
+
+   // ---- tensor-memory loads for the z work of plane k (the records were retired by the wait at the top of the
+   // step): issued here, consumed after the finish phase, so that their latency -- all eight warps ask at the
+   // same time -- is covered by the finish phase
+   TmVal tg[18], tq[14];
+   tm.template ld<0, 4>( tg, ph.c[4] ); tm.template ld<8, 2>( tg + 4, ph.c[4] );	// g1 g2 | g3 of plane k-2
+   tm.template ld<0, 4>( tg + 6, ph.c[3] ); tm.template ld<8, 2>( tg + 10, ph.c[3] );	// k-1
+   tm.template ld<0, 4>( tg + 12, ph.c[1] ); tm.template ld<8, 2>( tg + 16, ph.c[1] ); // k+1
+   tm.template ld<12, 2>( tq, ph.c[2] );	 // pr0A pr0B of plane k
+   tm.template ld<16, 8>( tq + 2, ph.c[2] );	 // pr1 pr2 e1 e2
+   tm.template ld<32, 4>( tq + 10, ph.c[2] ); // e4 e5
+
+   // ---- finish plane kf = k-1: difference its exchanged products (published by this step's barrier), one component
+   // at a time (7 pair loads in flight)
+   {
+      const double* const ex = c.sm + C::O_EX + EF * C::EX + c.ty * PX + 2 * c.txh + 2;
+      const double* const ey = c.sm + C::O_EY + EF * C::EY + ( c.ty + 2 ) * TX + 2 * c.txh;
+      const double* const d = c.sm + C::O_OP + ph.par * C::OPS + 2 * c.tid;
+      double fr[2] = { 0, 0 }, rinv[2] = { 0, 0 }; // PRED: dt^2/rho, 1/rho ; CORR: dt^4/(12 rho)
+      if( EPI != EPI_LU )
+      {
+	 const D2 e_rho = ld2( d );
+#pragma unroll
+	 for( int t = 0; t < 2; t++ )
+	 {
+	    const double rh = fin[t] ? pick( e_rho, t ) : 1.0;
+	    if( EPI == EPI_PRED )
+	    {
+	       rinv[t] = 1.0 / rh; // one division per point; dt^2/rho and acc/rho are formed from it
+	       fr[t] = a.fac * rinv[t];
+	    }
+	    else
+	       fr[t] = a.fac / rh;
+	 }
+      }
+      const double* const ring[3] = { &s.cu[R3][0], &s.cv[R3][0], &s.cw[R3][0] }; // plane kf = p-3
+#pragma unroll
+      for( int m = 0; m < 3; m++ )
+      {
+	 const D2 l = ld2( ex + m * TY * PX - 2 ), o = ld2( ex + m * TY * PX ), r = ld2( ex + m * TY * PX + 2 );
+	 const D2 m2 = ld2( ey + m * PY * TX - 2 * TX ), m1 = ld2( ey + m * PY * TX - TX ), p1 = ld2( ey + m * PY * TX + TX ),
+		  p2 = ld2( ey + m * PY * TX + 2 * TX );
+	 const double xd[2] = { d0u( l.x, l.y, o.y, r.x ), d0u( l.y, o.x, r.x, r.y ) };
+	 const double yd[2] = { d0u( m2.x, m1.x, p1.x, p2.x ), d0u( m2.y, m1.y, p1.y, p2.y ) };
+	 D2 e_um;
+	 e_um.x = e_um.y = 0;
+	 if( EPI != EPI_LU ) e_um = ld2( d + ( m + 1 ) * TX * TY );
+#pragma unroll
+	 for( int t = 0; t < 2; t++ )
+	 {
+	    double r_;
+	    if( m == 0 ) r_ = s.rp[0][t] + ( a.cof144 * sxo[t] ) * ( xd[t] + syo * yd[t] );
+	    else if( m == 1 ) r_ = s.rp[1][t] + ( a.cof144 * syo ) * ( sxo[t] * xd[t] + yd[t] );
+	    else r_ = s.rp[2][t] + a.cof144 * ( sxo[t] * xd[t] + syo * yd[t] );
+	    if( fin[t] )
+	    {
+	       if( EPI != EPI_LU && a.fo[0] ) r_ += a.fo[m][qf + t];
+	       if( EPI == EPI_LU )
+		  a.out[m][qf + t] = r_;
+	       else if( EPI == EPI_PRED )
+	       {
+		  a.out[m][qf + t] = 2 * ring[m][t] - pick( e_um, t ) + fr[t] * r_;
+		  if( a.out2[0] ) a.out2[m][qf + t] = r_ * rinv[t];
+	       }
+	       else
+		  a.out[m][qf + t] = pick( e_um, t ) + fr[t] * r_;
+	    }
+	 }
+      }
+   }
+   // ---- z pieces of plane k and its exchanged products
+   const double szk = k >= c.p0 ? c.sm[C::O_SZ + k - c.p0] : 0.0;
+   double rnew[3][2];
+   {
+      tm.template wait_ld<18>( tg );
+      tm.template wait_ld<14>( tq );
+      double t1[2], t2[2], t3[2];
+#pragma unroll
+      for( int t = 0; t < 2; t++ )
+      {
+	 t1[t] = d0u( tm_get( tg[0 + t] ), tm_get( tg[6 + t] ), tm_get( tg[12 + t] ), g1n[t] );
+	 t2[t] = d0u( tm_get( tg[2 + t] ), tm_get( tg[8 + t] ), tm_get( tg[14 + t] ), g2n[t] );
+	 t3[t] = d0u( tm_get( tg[4 + t] ), tm_get( tg[10 + t] ), tm_get( tg[16 + t] ), g3n[t] );
+      }
+      const double c144z = a.cof144 * szk;
+      double e1[2], e2[2], e3[2], e4[2], e5[2], e6[2];
+#pragma unroll
+      for( int t = 0; t < 2; t++ )
+      {
+	 const double prk0 = tm_get( tq[0 + t] ), prk1 = tm_get( tq[2 + t] ), prk2 = tm_get( tq[4 + t] );
+	 const double e1k = tm_get( tq[6 + t] ), e2k = tm_get( tq[8 + t] ), e4k = tm_get( tq[10 + t] ), e5k = tm_get( tq[12 + t] );
+	 const W4 wmz = weights4( s.amz[R4][t], s.amz[R3][t], s.amz[R2][t], s.amz[R1][t], s.amz[R0][t] );
+	 const W4 wlz = weights4( s.alz[R4][t], s.alz[R3][t], s.alz[R2][t], s.alz[R1][t], s.alz[R0][t] );
+	 const double rz0 = prk0 + szk * gsum( wmz, s.cu[R4][t], s.cu[R3][t], s.cu[R2][t], s.cu[R1][t], s.cu[R0][t] );
+	 const double rz1 = prk1 + szk * gsum( wmz, s.cv[R4][t], s.cv[R3][t], s.cv[R2][t], s.cv[R1][t], s.cv[R0][t] );
+	 const double rz2 = prk2 + szk * gsum( wlz, s.cw[R4][t], s.cw[R3][t], s.cw[R2][t], s.cw[R1][t], s.cw[R0][t] );
+	 const double dzu = d0u( s.cu[R4][t], s.cu[R3][t], s.cu[R1][t], s.cu[R0][t] );
+	 const double dzv = d0u( s.cv[R4][t], s.cv[R3][t], s.cv[R1][t], s.cv[R0][t] );
+	 const double dzw = d0u( s.cw[R4][t], s.cw[R3][t], s.cw[R1][t], s.cw[R0][t] );
+	 const double msz = s.amz[R2][t];		   // mu sz of plane k
+	 const double lzw = ( s.alz[R2][t] - 2 * msz ) * dzw; // la sz D0z w
+	 e1[t] = e1k + lzw;
+	 e2[t] = e2k;
+	 e3[t] = msz * dzu;
+	 e4[t] = e4k;
+	 e5[t] = e5k + lzw;
+	 e6[t] = msz * dzv;
+	 rnew[0][t] = a.cof6 * rz0 + ( c144z * sxo[t] ) * t1[t];
+	 rnew[1][t] = a.cof6 * rz1 + ( c144z * syo ) * t2[t];
+	 rnew[2][t] = a.cof6 * rz2 + c144z * t3[t];
+      }
+      double* const ex = c.sm + C::O_EX + EB * C::EX + c.ty * PX + 2 * c.txh + 2;
+      double* const ey = c.sm + C::O_EY + EB * C::EY + ( c.ty + 2 ) * TX + 2 * c.txh;
+      st2( ex, e1[0], e1[1] );
+      st2( ex + TY * PX, e2[0], e2[1] );
+      st2( ex + 2 * TY * PX, e3[0], e3[1] );
+      st2( ey, e4[0], e4[1] );
+      st2( ey + PY * TX, e5[0], e5[1] );
+      st2( ey + 2 * PY * TX, e6[0], e6[1] );
+
+      // ring of width 2 around the tile: the same products recomputed from the staged planes
+      // (plane k sits in slot R2, k-2..k+2 in R4..R0); mu, la of the ring points from the side copy
+      for( int hh = c.tid; hh < NH; hh += NT )
+      {
+	 const double* const sf = c.sm + C::O_UVW;
+	 double* const hml = c.sm + C::O_HML;
+	 int sx_, sy_;
+	 if( hh < 4 * TY )
+	 {
+	    const int hx = hh & 3, row = hh >> 2;
+	    sx_ = hx < 2 ? hx : TX + hx; sy_ = row + 2;
+	 }
+	 else
+	 {
+	    const int t = hh - 4 * TY;
+	    const int hy = t >> 5, col = t & 31;
+	    sy_ = hy < 2 ? hy : TY + hy; sx_ = col + 2;
+	 }
+	 const int oo = sy_ * PX + sx_;
+	 hml[ph.t0 + hh] = c.sm[C::O_ML + ( 0 * 2 + ML ) * PLANE + oo];
+	 hml[ph.t0 + NH + hh] = c.sm[C::O_ML + ( 1 * 2 + ML ) * PLANE + oo];
+	 const double hm = hml[ph.t2 + hh], hl = hml[ph.t2 + NH + hh];
+	 const double* const qu = sf + 0 * NSLOT * PLANE + ph.o[2] + oo;
+	 const double* const qv = sf + 1 * NSLOT * PLANE + ph.o[2] + oo;
+	 const double hdzw = d0u( sf[2 * NSLOT * PLANE + ph.o[4] + oo], sf[2 * NSLOT * PLANE + ph.o[3] + oo],
+				  sf[2 * NSLOT * PLANE + ph.o[1] + oo], sf[2 * NSLOT * PLANE + ph.o[0] + oo] );
+	 if( hh < 4 * TY )
+	 {
+	    const double hdyv = d0u( qv[-2 * PX], qv[-PX], qv[PX], qv[2 * PX] );
+	    const double hdyu = d0u( qu[-2 * PX], qu[-PX], qu[PX], qu[2 * PX] );
+	    const double hdzu = d0u( sf[0 * NSLOT * PLANE + ph.o[4] + oo], sf[0 * NSLOT * PLANE + ph.o[3] + oo],
+				     sf[0 * NSLOT * PLANE + ph.o[1] + oo], sf[0 * NSLOT * PLANE + ph.o[0] + oo] );
+	    double* const hx_ = c.sm + C::O_EX + EB * C::EX + ( sy_ - 2 ) * PX + sx_;
+	    hx_[0] = hl * ( c.sm[C::O_SY + sy_] * hdyv + szk * hdzw );
+	    hx_[TY * PX] = hm * hdyu;
+	    hx_[2 * TY * PX] = ( hm * szk ) * hdzu;
+	 }
+	 else
+	 {
+	    const double hdxv = d0u( qv[-2], qv[-1], qv[1], qv[2] );
+	    const double hdxu = d0u( qu[-2], qu[-1], qu[1], qu[2] );
+	    const double hdzv = d0u( sf[1 * NSLOT * PLANE + ph.o[4] + oo], sf[1 * NSLOT * PLANE + ph.o[3] + oo],
+				     sf[1 * NSLOT * PLANE + ph.o[1] + oo], sf[1 * NSLOT * PLANE + ph.o[0] + oo] );
+	    double* const hy_ = c.sm + C::O_EY + EB * C::EY + sy_ * TX + ( sx_ - 2 );
+	    hy_[0] = hm * hdxv;
+	    hy_[PY * TX] = hl * ( c.sm[C::O_SX + sx_] * hdxu + szk * hdzw );
+	    hy_[2 * PY * TX] = ( hm * szk ) * hdzv;
+	 }
+      }
+   }
+
+#pragma unroll
+   for( int m = 0; m < 3; m++ ) { s.rp[m][0] = rnew[m][0]; s.rp[m][1] = rnew[m][1]; }
+}
+
+} // namespace fast4
+
+template <int TY, int EPI>
+__global__ void __launch_bounds__( 16 * TY, 1 ) k_rhs_fast4( const FastArgs a )
+{
+   using namespace fast4;
+   typedef fast4::Cfg<TY> C;
+   constexpr int TX = C::TX, PX = C::PX, PY = C::PY, PLANE = C::PLANE, NT = C::NT;
+   SW4_DYN_SMEM( smem );
+   fast4::Ctx<TY> c;
+   c.sm = smem;
+
+   const Block& b = a.b;
+   c.tid = threadIdx.x;
+   asm volatile( "" : "+r"( c.tid ) ); // (keeps ptxas from re-reading SR_TID in every step: a long-scoreboard wait)
+   c.txh = c.tid & 15; c.ty = c.tid >> 4;
+   const int li0 = 2 + blockIdx.x * TX, lj0 = 2 + blockIdx.y * TY; // local (array) index of the tile's first output
+   c.li0 = li0; c.lj0 = lj0;
+   c.ka = a.klo + blockIdx.z * a.kchunk;
+   c.kb = ( c.ka + a.kchunk - 1 < a.khi ) ? c.ka + a.kchunk - 1 : a.khi;
+   if( c.ka > c.kb ) return;
+   c.pend = c.kb + 2;
+
+   fast4::Tm tm;
+   if( c.tid == 0 )
+   {
+      constexpr int NCP = C::NCP_PLANE + ( EPI != EPI_LU ? C::NCP_OPS : 0 );
+      mbar_init( smem + C::O_MBAR, NCP );
+      mbar_init( smem + C::O_MBAR + 1, NCP );
+#if !defined( SW4B200_EMULATE )
+      asm volatile( "fence.mbarrier_init.release.cluster;" ::: "memory" );
+#endif
+   }
+#if !defined( SW4B200_EMULATE )
+   // all 512 columns of tensor memory: one CTA per SM (shared memory), so nobody else can want them
+   uint32_t* const tm_slot = reinterpret_cast<uint32_t*>( smem + C::O_MBAR + 2 );
+   if( c.tid < 32 )
+   {
+      asm volatile( "tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"( (uint32_t)__cvta_generic_to_shared( tm_slot ) )
+		    : "memory" );
+      asm volatile( "tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory" );
+   }
+#endif
+
+   for( int t = c.tid; t < PX + PY; t += NT )
+   {
+      if( t < PX )
+      {
+	 const int li = li0 - 2 + t;
+	 smem[C::O_SX + t] = li < b.ni ? a.strx[li] : 0.0;
+      }
+      else
+      {
+	 const int lj = lj0 - 2 + ( t - PX );
+	 smem[C::O_SY + t - PX] = lj < b.nj ? a.stry[lj] : 0.0;
+      }
+   }
+   c.p0 = c.ka - 2;
+   for( int t = c.tid; t <= c.kb + 3 - c.p0; t += NT )
+   {
+      int kp = c.p0 + t - b.kfirst;
+      kp = kp > b.nk - 1 ? b.nk - 1 : kp;
+      smem[C::O_SZ + t] = a.strz[kp];
+   }
+   for( int t = c.tid; t < 6 * C::NH; t += NT ) smem[C::O_HML + t] = 0.0;
+   c.o = ( c.ty + 2 ) * PX + 2 * c.txh + 2; // left own point in a staged plane
+   const int li = li0 + 2 * c.txh, lj = lj0 + c.ty;
+   c.act[0] = li <= b.ni - 3 && lj <= b.nj - 3;
+   c.act[1] = li + 1 <= b.ni - 3 && lj <= b.nj - 3;
+   c.gown = (long long)lj * b.ni + li;
+
+   fast4::State s;
+#pragma unroll
+   for( int m = 0; m < 5; m++ )
+#pragma unroll
+      for( int t = 0; t < 2; t++ ) s.cu[m][t] = s.cv[m][t] = s.cw[m][t] = s.amz[m][t] = s.alz[m][t] = 0;
+#pragma unroll
+   for( int m = 0; m < 3; m++ ) s.rp[m][0] = s.rp[m][1] = 0;
+
+#if !defined( SW4B200_EMULATE )
+   asm volatile( "tcgen05.fence::before_thread_sync;" ::: "memory" );
+   __syncthreads(); // tensor-memory address, s_sx, s_sy visible
+   asm volatile( "tcgen05.fence::after_thread_sync;" ::: "memory" );
+   const uint32_t tm_alloc = *tm_slot;
+   {
+      const int w = c.tid >> 5; // warp w owns lanes 32 (w%4)..+31 and the (w/4)-th column range
+      tm.base = tm_alloc + ( (uint32_t)( ( w & 3 ) * 32 ) << 16 ) + (uint32_t)( ( w >> 2 ) * C::COLS );
+   }
+#else
+   __syncthreads();
+#endif
+   {
+      // records of the planes before the first one read as zero, like the register rings above
+      const double z[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+      tm.template st<0 * C::REC, 8>( z ); tm.template st<0 * C::REC + 16, 8>( z ); tm.template st<0 * C::REC + 32, 4>( z );
+      tm.template st<1 * C::REC, 8>( z ); tm.template st<1 * C::REC + 16, 8>( z ); tm.template st<1 * C::REC + 32, 4>( z );
+      tm.template st<2 * C::REC, 8>( z ); tm.template st<2 * C::REC + 16, 8>( z ); tm.template st<2 * C::REC + 32, 4>( z );
+      tm.template st<3 * C::REC, 8>( z ); tm.template st<3 * C::REC + 16, 8>( z ); tm.template st<3 * C::REC + 32, 4>( z );
+      tm.template st<4 * C::REC, 8>( z ); tm.template st<4 * C::REC + 16, 8>( z ); tm.template st<4 * C::REC + 32, 4>( z );
+      tm.template st<5 * C::REC, 8>( z ); tm.template st<5 * C::REC + 16, 8>( z ); tm.template st<5 * C::REC + 32, 4>( z );
+      tm.wait_st();
+   }
+
+   const int plast = c.kb + 3; // one extra step finishes plane kb
+   fast4::Ph ph;
+   {
+      const int p = c.ka - 2;
+      int m6 = p % 6, m3 = p % 3;
+      m6 = m6 < 0 ? m6 + 6 : m6; m3 = m3 < 0 ? m3 + 3 : m3;
+      ph.slot = m6;
+#pragma unroll
+      for( int j = 0; j < 5; j++ )
+      {
+	 const int sj = ( m6 + 6 - j ) % 6;
+	 ph.o[j] = PLANE * sj; ph.c[j] = C::REC * sj;
+      }
+      ph.par = p & 1;
+      ph.wpar = 0;
+      ph.t0 = 2 * C::NH * m3; ph.t2 = 2 * C::NH * ( ( m3 + 1 ) % 3 );
+      fast4::stage<TY, EPI>( a, c, p, ph.slot, ph.par );
+   }
+   for( int p = c.ka - 2; p <= plast; p++ )
+   {
+      fast4::step<TY, EPI>( a, c, s, tm, p, ph );
+      // next plane
+      ph.slot = ph.slot == 5 ? 0 : ph.slot + 1;
+#pragma unroll
+      for( int j = 4; j > 0; j-- ) { ph.o[j] = ph.o[j - 1]; ph.c[j] = ph.c[j - 1]; }
+      ph.o[0] = PLANE * ph.slot; ph.c[0] = C::REC * ph.slot;
+      ph.wpar ^= 1 << ph.par; // the barrier just consumed flips its phase
+      ph.par ^= 1;
+      ph.t2 = ( ph.t0 == 0 ? 2 : ( ph.t0 == 2 * C::NH ? 0 : 1 ) ) * 2 * C::NH; // slot of plane (p+1)-2 = slot of p+2 mod 3
+      ph.t0 = ph.t0 == 4 * C::NH ? 0 : ph.t0 + 2 * C::NH;
+   }
+#if !defined( SW4B200_EMULATE )
+   // every warp is done with its strip (its loads were waited for) before the columns go back
+   asm volatile( "tcgen05.fence::before_thread_sync;" ::: "memory" );
+   __syncthreads();
+   if( c.tid < 32 ) asm volatile( "tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"( tm_alloc ) : "memory" );
+#endif
+}
+
+#ifndef SW4B200_EMULATE
+namespace {
+template <int TY, int EPI>
+int launch_fast4_t( FastArgs a, cudaStream_t st )
+{
+   typedef fast4::Cfg<TY> C;
+   static bool configured = false;
+   const size_t smem = C::SMEM_DOUBLES * sizeof( double );
+   if( !configured )
+   {
+      cudaError_t e = cudaFuncSetAttribute( k_rhs_fast4<TY, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem );
+      if( e != cudaSuccess ) return set_error( "k_rhs_fast4: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString( e ) );
+      configured = true;
+   }
+   if( a.kchunk <= 0 ) a.kchunk = fast_kchunk( a.b, a.khi - a.klo + 1, TY );
+   if( a.kchunk > C::SZMAX - 6 ) a.kchunk = C::SZMAX - 6;
+   const Block& b = a.b;
+   dim3 bs( C::NT, 1, 1 );
+   dim3 gs( ( b.ni - 4 + C::TX - 1 ) / C::TX, ( b.nj - 4 + TY - 1 ) / TY, ( a.khi - a.klo + 1 + a.kchunk - 1 ) / a.kchunk );
+   ProfScope prof( EPI == EPI_PRED ? "rhs_fast_pred" : ( EPI == EPI_CORR ? "rhs_fast_corr" : "rhs_fast_lu" ), st );
+   k_rhs_fast4<TY, EPI><<<gs, bs, smem, st>>>( a );
+   count_launch();
+   return check_launch( "k_rhs_fast4" );
+}
+} // namespace
+
+int launch_fast2( int epi, FastArgs a, cudaStream_t st );
+
+int launch_fast4( int epi, const FastArgs& a, cudaStream_t st )
+{
+   if( a.khi < a.klo ) return 0;
+   // the row copies need 16-byte aligned rows: even ni and 16-byte aligned arrays.  The reference's own inputs give odd
+   // ni (205, 305, 605 + 4 ghost points ...): those grids take the cp.async kernel of the second generation.
+   uintptr_t al = (uintptr_t)a.u[0] | (uintptr_t)a.u[1] | (uintptr_t)a.u[2] | (uintptr_t)a.mu | (uintptr_t)a.la;
+   if( epi != EPI_LU ) al |= (uintptr_t)a.rho | (uintptr_t)a.um[0] | (uintptr_t)a.um[1] | (uintptr_t)a.um[2];
+   if( ( a.b.ni & 1 ) || ( al & 15 ) ) return launch_fast2( epi, a, st );
+   switch( epi )
+   {
+   case EPI_LU: return launch_fast4_t<16, EPI_LU>( a, st );
+   case EPI_PRED: return launch_fast4_t<16, EPI_PRED>( a, st );
+   default: return launch_fast4_t<16, EPI_CORR>( a, st );
+   }
+}
+#endif
+
+} // namespace sw4b200

@@ -3,6 +3,7 @@
 #include "rhs4sg_fast.cu"
 #include "rhs4sg_fast2.cu"
 #include "rhs4sg_fast3.cu"
+#include "rhs4sg_fast4.cu"
 #include "addsgd_fast.cu"
 #include "curvilinear.cu"
 #include "api.cu"

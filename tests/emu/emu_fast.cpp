@@ -10,6 +10,7 @@ std::barrier<>* g_barrier = 0;
 #include "../../sw4lite_b200/csrc/rhs4sg_fast.cu"
 #include "../../sw4lite_b200/csrc/rhs4sg_fast2.cu"
 #include "../../sw4lite_b200/csrc/rhs4sg_fast3.cu"
+#include "../../sw4lite_b200/csrc/rhs4sg_fast4.cu"
 
 using namespace sw4b200;
 
@@ -43,6 +44,17 @@ extern "C" int emu_rhs_fast( int gen, int epi, int ifirst, int ilast, int jfirst
       a.fo[c] = fo ? fo + c * n : 0;
    }
    a.mu = mu; a.la = la; a.strx = strx; a.stry = stry; a.strz = strz; a.cof6 = cof / 6; a.cof144 = cof / 144; a.rho = rho; a.fac = fac;
+   if( gen == 4 )
+   {
+      constexpr int TY4 = 16;
+      typedef fast4::Cfg<TY4> C4;
+      dim3 bs( C4::NT, 1, 1 );
+      dim3 gs( ( a.b.ni - 4 + C4::TX - 1 ) / C4::TX, ( a.b.nj - 4 + TY4 - 1 ) / TY4, ( khi - klo + 1 + kchunk - 1 ) / kchunk );
+      if( epi == EPI_LU ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_LU>( a ); } );
+      else if( epi == EPI_PRED ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_PRED>( a ); } );
+      else emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_CORR>( a ); } );
+      return 0;
+   }
    if( gen >= 3000 )
    {
       switch( gen - 3000 )

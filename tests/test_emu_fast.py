@@ -18,15 +18,16 @@ SRC = [os.path.join(EMU, "emu_fast.cpp"), os.path.join(EMU, "cuda_emu.h"),
        os.path.join(HERE, "..", "sw4lite_b200", "csrc", "rhs4sg_fast.cu"),
        os.path.join(HERE, "..", "sw4lite_b200", "csrc", "rhs4sg_fast2.cu"),
        os.path.join(HERE, "..", "sw4lite_b200", "csrc", "rhs4sg_fast3.cu"),
+       os.path.join(HERE, "..", "sw4lite_b200", "csrc", "rhs4sg_fast4.cu"),
        os.path.join(HERE, "..", "sw4lite_b200", "csrc", "common.cuh")]
 _dp = C.POINTER(C.c_double)
 GEN = 2  # generation of the fast kernel under test, set per test by the fixture below
 
 
-@pytest.fixture(autouse=True, params=[2, 3122, 3121, 3082], ids=["fast2", "fast3-12w-tm2", "fast3-12w-tm1", "fast3-8w-tm2"])
+@pytest.fixture(autouse=True, params=[4, 2, 3122, 3082], ids=["fast4-pairs", "fast2", "fast3-12w-tm2", "fast3-8w-tm2"])
 def generation(request):
-    """2: rhs4sg_fast2.cu; 3000+10*TY+TMODE: rhs4sg_fast3.cu (the product path is 3122: 32x12 tile, z delay lines
-    and g rings in tensor memory -- emulated here as a per-thread array)"""
+    """4: rhs4sg_fast4.cu (x-pair register blocking, z state in tensor memory -- emulated here as a per-thread
+    array); 2: rhs4sg_fast2.cu; 3000+10*TY+TMODE: rhs4sg_fast3.cu"""
     global GEN
     GEN = request.param
     yield
@@ -46,6 +47,12 @@ def d(a):
     return a.ctypes.data_as(_dp) if a is not None else None
 
 
+def even(dims):
+    """the fourth generation stages rows with 16-byte bulk copies: ni (= nx + 4 ghost points) must be even; odd
+    grids are served by the second generation (launch_fast4 dispatches)"""
+    return ((dims[0] + 1) // 2 * 2,) + tuple(dims[1:]) if GEN == 4 else dims
+
+
 def run(emu, epi, box, klo, khi, kchunk, f, cof, out, out2=None, um=None, rho=None, fo=None, fac=0.0):
     emu.emu_rhs_fast(GEN, epi, *box.bounds, klo, khi, kchunk, d(f["u"]), d(f["mu"]), d(f["la"]), d(f["strx"]), d(f["stry"]),
                      d(f["strz"]), cof, d(out), d(out2), d(um), d(rho), d(fo), fac)
@@ -62,7 +69,7 @@ def cpu_lu(box, f, h, onesided=(0,) * 6, nk=None):
 
 @pytest.mark.parametrize("dims,kchunk", [((45, 22, 20), 16), ((37, 13, 23), 7), ((70, 9, 9), 5)])
 def test_emu_lu_matches_oracle(emu, dims, kchunk):
-    box = Box(*dims)
+    box = Box(*even(dims))
     f = random_fields(box, seed=21)
     h = 0.7
     ref = cpu_lu(box, f, h)
@@ -76,7 +83,7 @@ def test_emu_lu_matches_oracle(emu, dims, kchunk):
 
 def test_emu_row_range_between_closures(emu):
     """rows 7..nk-6 only (the closure rows belong to another kernel)"""
-    box = Box(40, 20, 26)
+    box = Box(*even((40, 20, 26)))
     nk = box.nk - 4
     f = random_fields(box, seed=22)
     ref = cpu_lu(box, f, 1.0, onesided=(0, 0, 0, 0, 1, 1)).reshape(3, box.nk, box.nj, box.ni)
@@ -89,7 +96,7 @@ def test_emu_row_range_between_closures(emu):
 
 
 def test_emu_predictor_and_corrector_epilogues(emu):
-    box = Box(41, 19, 15)
+    box = Box(*even((41, 19, 15)))
     f = random_fields(box, seed=23)
     h, dt = 0.4, 0.05
     O = oracle()
