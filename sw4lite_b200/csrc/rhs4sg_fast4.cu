@@ -28,8 +28,26 @@
 //
 // Also compiled by g++ (SW4B200_EMULATE) for the CPU check of the kernel source (tests/emu).
 #include "common.cuh"
+#include <cstring>
+#ifndef SW4B200_EMULATE
+#include <cuda.h> // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, libcuda is not linked)
+#endif
 
 namespace sw4b200 {
+
+// TMA descriptors of the arrays one launch reads: 3-D tensors (ni, nj, nk) of doubles, boxes of one tile plane
+#if defined( SW4B200_EMULATE )
+struct TMap { const double* base; };
+#define SW4_GRID_CONSTANT
+#else
+typedef CUtensorMap TMap;
+#define SW4_GRID_CONSTANT __grid_constant__
+#endif
+struct FastMaps
+{
+   TMap u[3], mu, la; // boxes PX x PY x 1 (tile plane with its ring)
+   TMap rho, um[3];   // boxes TX x TY x 1 (own points)
+};
 
 namespace fast4 {
 
@@ -54,15 +72,22 @@ __device__ __forceinline__ void st2( double* p, double x, double y )
    *reinterpret_cast<D2*>( p ) = v;
 }
 
-// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: rows of a plane go from global to
-// shared memory without passing through registers, the LSU queue or per-thread address arithmetic
+// ---- TMA tile loads (cp.async.bulk.tensor, SASS UTMALDG) completing on an mbarrier: one request moves a whole
+// BX x BY plane box from global to shared memory -- no registers, no LSU queue, no per-thread address arithmetic,
+// out-of-array elements arrive as zeros
 #if defined( SW4B200_EMULATE )
 __device__ __forceinline__ void mbar_init( double*, int ) {}
 __device__ __forceinline__ void mbar_arrive_expect( double*, int ) {}
 __device__ __forceinline__ void mbar_wait( double*, int ) {}
-__device__ __forceinline__ void bulk_copy( double* dst, const double* src, int bytes, double* )
+template <int BX, int BY>
+__device__ __forceinline__ void tma_tile( double* dst, const TMap* map, const Block& b, int c0, int c1, int c2, double* )
 {
-   for( int i = 0; i < bytes / 8; i++ ) dst[i] = src[i];
+   for( int y = 0; y < BY; y++ )
+      for( int x = 0; x < BX; x++ )
+      {
+	 const int i = c0 + x, j = c1 + y;
+	 dst[y * BX + x] = ( i >= 0 && i < b.ni && j >= 0 && j < b.nj && c2 >= 0 && c2 < b.nk ) ? map->base[b.nij * c2 + (long long)j * b.ni + i] : 0.0;
+      }
 }
 #else
 __device__ __forceinline__ void mbar_init( double* mbar, int count )
@@ -87,12 +112,13 @@ __device__ __forceinline__ void mbar_wait( double* mbar, int parity )
 		 "r"( parity )
 		 : "memory" );
 }
-// bytes: multiple of 16; dst, src 16-byte aligned
-__device__ __forceinline__ void bulk_copy( double* dst, const double* src, int bytes, double* mbar )
+// dst 128-byte aligned; the box dimensions are those of the descriptor
+template <int BX, int BY>
+__device__ __forceinline__ void tma_tile( double* dst, const TMap* map, const Block&, int c0, int c1, int c2, double* mbar )
 {
-   asm volatile( "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+   asm volatile( "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
 		     (uint32_t)__cvta_generic_to_shared( dst ) ),
-		 "l"( src ), "r"( bytes ), "r"( (uint32_t)__cvta_generic_to_shared( mbar ) )
+		 "l"( map ), "r"( c0 ), "r"( c1 ), "r"( c2 ), "r"( (uint32_t)__cvta_generic_to_shared( mbar ) )
 		 : "memory" );
 }
 #endif
@@ -102,23 +128,22 @@ struct Cfg
 {
    static constexpr int TXP = 16, TX = 2 * TXP, PX = TX + 4, PY = TY + 4, PLANE = PX * PY, NT = TXP * TY, NSLOT = 6;
    static constexpr int NH = 4 * TY + 4 * TX; // ring points of the tile per plane
-   static constexpr int NCP_PLANE = 5 * PY, NCP_OPS = 4 * TY; // row copies per plane: u,v,w,mu,la rows ; rho,um rows
    static constexpr int EX = 3 * TY * PX, EY = 3 * PY * TX;
    static constexpr int OPS = 4 * TX * TY; // epilogue operands of one plane: rho, um[3] of the own points
    static constexpr int SZMAX = 512;	   // strz of the planes a CTA marches through (kchunk + 6 <= SZMAX)
    // shared memory, in doubles (every region starts on a 16-byte boundary)
    static constexpr int O_UVW = 0;			      // [3][NSLOT][PLANE]
    static constexpr int O_ML = O_UVW + 3 * NSLOT * PLANE;     // [2][2][PLANE]   mu, la of the arriving plane
-   static constexpr int O_EX = O_ML + 4 * PLANE;	      // [2][3][TY][PX]  E1..E3, double buffered
+   static constexpr int O_OP = O_ML + 4 * PLANE;	      // [2][4][TX*TY]   rho, um of the own points (TMA destinations first:
+   static constexpr int O_EX = O_OP + 2 * OPS;		      // [2][3][TY][PX]  E1..E3, double buffered        128-byte aligned)
    static constexpr int O_EY = O_EX + 2 * EX;		      // [2][3][PY][TX]  E4..E6
    static constexpr int O_HML = O_EY + 2 * EY;		      // [3][2][NH]      mu, la of the ring points, planes p-2..p
    static constexpr int O_SX = O_HML + 6 * NH;		      // [PX]
    static constexpr int O_SY = O_SX + PX;		      // [PY]
-   static constexpr int O_OP = O_SY + PY;		      // [2][4][TX*TY]
-   static constexpr int O_SZ = O_OP + 2 * OPS;		      // [SZMAX]
+   static constexpr int O_SZ = O_SY + PY;		      // [SZMAX]
    static constexpr int O_MBAR = O_SZ + SZMAX;		      // two mbarriers (even / odd planes)
    static constexpr int SMEM_DOUBLES = O_MBAR + 2 + 2;	      // + the tensor-memory base address
-   static_assert( NCP_PLANE + NCP_OPS <= NT, "one row copy per thread" );
+   static_assert( ( PLANE % 16 ) == 0 && ( O_ML % 16 ) == 0 && ( O_OP % 16 ) == 0 && ( ( TX * TY ) % 16 ) == 0, "TMA destinations: 128-byte aligned" );
    static constexpr int REC = 40;			      // tensor-memory columns per plane record
    static constexpr int COLS = 256;			      // columns per warp of a lane quadrant (8 warps)
    static_assert( NT == 256, "8 warps: two per tensor-memory lane quadrant" );
@@ -160,50 +185,38 @@ struct Ph
    int t0, t2; // 2 NH (p mod 3), 2 NH ((p-2) mod 3): side copies of the ring points' mu, la
 };
 
-// stage plane p: every thread below NCP issues ONE row copy (TMA bulk copy, completing on the mbarrier of the plane's
-// parity): rows of u,v,w into ring slot `slot`, rows of mu,la into slot `par`; with an epilogue also the own-row
-// operands (rho, um) of plane p-3, the plane that the step handling plane p finishes, into operand buffer `par`.
-// Requires 16-byte aligned rows: ni even, array bases 16-byte aligned (launch_fast4 checks; other grids take the
-// cp.async kernel rhs4sg_fast2.cu).  Out-of-array parts of the tile are not filled: only points outside the
-// interior ever read them, and those are never stored.
+// stage plane p (one thread): TMA tile loads completing on the mbarrier of the plane's parity: the PX x PY boxes of u,v,w
+// into ring slot `slot`, of mu,la into slot `par`; with an epilogue also the TX x TY boxes of the own-point operands
+// (rho, um) of plane p-3, the plane that the step handling plane p finishes, into operand buffer `par`.
+// Requires ni even and 16-byte aligned arrays (tensor-map strides; launch_fast4 checks, other grids take the cp.async
+// kernel rhs4sg_fast2.cu).
 template <int TY, int EPI>
-__device__ __forceinline__ void stage( const FastArgs& a, const Ctx<TY>& c, int p, int slot, int par )
+__device__ __forceinline__ void stage( const FastArgs& a, const FastMaps& maps, const Ctx<TY>& c, int p, int slot, int par )
 {
    typedef Cfg<TY> C;
-   constexpr int NCP = C::NCP_PLANE + ( EPI != EPI_LU ? C::NCP_OPS : 0 );
-   if( p > c.pend + 1 || c.tid >= NCP ) return;
+   if( p > c.pend + 1 || c.tid != 0 ) return;
    const Block& b = a.b;
    double* const mbar = c.sm + C::O_MBAR + par;
-   const double* src = 0;
-   double* dst = 0;
-   int n = 0; // doubles
-   if( c.tid < C::NCP_PLANE )
+   const int kq = p - 3;
+   const bool plane = p <= c.pend; // (the step after the last plane only finishes plane kb)
+   const bool ops = EPI != EPI_LU && kq >= c.ka && kq <= c.kb;
+   mbar_arrive_expect( mbar, ( plane ? 5 * C::PLANE * 8 : 0 ) + ( ops ? 4 * C::TX * TY * 8 : 0 ) );
+   if( plane )
    {
-      const int f = c.tid / C::PY, row = c.tid - f * C::PY;
-      const int lj = c.lj0 - 2 + row, li = c.li0 - 2;
-      if( p <= c.pend && lj < b.nj ) // (the step after the last plane only finishes plane kb)
-      {
-	 n = b.ni - li < C::PX ? b.ni - li : C::PX;
-	 const long long g = b.nij * ( p - b.kfirst ) + (long long)lj * b.ni + li;
-	 src = ( f == 0 ? a.u[0] : f == 1 ? a.u[1] : f == 2 ? a.u[2] : f == 3 ? a.mu : a.la ) + g;
-	 dst = c.sm + ( f < 3 ? C::O_UVW + ( f * C::NSLOT + slot ) * C::PLANE : C::O_ML + ( ( f - 3 ) * 2 + par ) * C::PLANE ) + row * C::PX;
-      }
+      const int c0 = c.li0 - 2, c1 = c.lj0 - 2, c2 = p - b.kfirst;
+#pragma unroll
+      for( int f = 0; f < 3; f++ )
+	 tma_tile<C::PX, C::PY>( c.sm + C::O_UVW + ( f * C::NSLOT + slot ) * C::PLANE, &maps.u[f], b, c0, c1, c2, mbar );
+      tma_tile<C::PX, C::PY>( c.sm + C::O_ML + ( 0 * 2 + par ) * C::PLANE, &maps.mu, b, c0, c1, c2, mbar );
+      tma_tile<C::PX, C::PY>( c.sm + C::O_ML + ( 1 * 2 + par ) * C::PLANE, &maps.la, b, c0, c1, c2, mbar );
    }
-   else if( EPI != EPI_LU )
+   if( ops )
    {
-      const int t = c.tid - C::NCP_PLANE;
-      const int f = t / TY, row = t - f * TY;
-      const int lj = c.lj0 + row, kq = p - 3;
-      if( kq >= c.ka && kq <= c.kb && lj < b.nj && c.li0 < b.ni )
-      {
-	 n = b.ni - c.li0 < C::TX ? b.ni - c.li0 : C::TX;
-	 const long long g = b.nij * ( kq - b.kfirst ) + (long long)lj * b.ni + c.li0;
-	 src = ( f == 0 ? a.rho : a.um[f - 1] ) + g;
-	 dst = c.sm + C::O_OP + par * C::OPS + f * C::TX * TY + row * C::TX;
-      }
+      double* const d = c.sm + C::O_OP + par * C::OPS;
+      tma_tile<C::TX, TY>( d, &maps.rho, b, c.li0, c.lj0, kq - b.kfirst, mbar );
+#pragma unroll
+      for( int m = 0; m < 3; m++ ) tma_tile<C::TX, TY>( d + ( m + 1 ) * C::TX * TY, &maps.um[m], b, c.li0, c.lj0, kq - b.kfirst, mbar );
    }
-   mbar_arrive_expect( mbar, 8 * n );
-   if( n > 0 ) bulk_copy( dst, src, 8 * n, mbar );
 }
 
 __device__ __forceinline__ double pick( const D2& v, int t ) { return t ? v.y : v.x; }
@@ -212,7 +225,7 @@ __device__ __forceinline__ double pick( const D2& v, int t ) { return t ? v.y : 
 // the z work of plane k=p-2 (publishing its exchanged products in E buffer S&1) and finishes plane k-1
 // (reading E buffer (S+1)&1).
 template <int TY, int EPI>
-__device__ __forceinline__ void step( const FastArgs& a, Ctx<TY>& c, State& s, Tm& tm, const int p, const Ph& ph )
+__device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, Ctx<TY>& c, State& s, Tm& tm, const int p, const Ph& ph )
 {
    typedef Cfg<TY> C;
    constexpr int TX = C::TX, PX = C::PX, PY = C::PY, PLANE = C::PLANE, NT = C::NT, NSLOT = C::NSLOT, NH = C::NH;
@@ -224,7 +237,7 @@ __device__ __forceinline__ void step( const FastArgs& a, Ctx<TY>& c, State& s, T
 
    mbar_wait( c.sm + C::O_MBAR + ph.par, ( ph.wpar >> ph.par ) & 1 ); // the rows of plane p have landed
    __syncthreads(); // the E products of plane k-1 are visible; slot of plane p-5 is free
-   stage<TY, EPI>( a, c, p + 1, ph.slot == NSLOT - 1 ? 0 : ph.slot + 1, ph.par ^ 1 );
+   stage<TY, EPI>( a, maps, c, p + 1, ph.slot == NSLOT - 1 ? 0 : ph.slot + 1, ph.par ^ 1 );
    tm.wait_st(); // the records stored by the earlier steps (long done) are readable
 
    const bool kfin = kf >= c.ka && kf <= c.kb;
@@ -520,12 +533,17 @@ __device__ __forceinline__ void step( const FastArgs& a, Ctx<TY>& c, State& s, T
 } // namespace fast4
 
 template <int TY, int EPI>
-__global__ void __launch_bounds__( 16 * TY, 1 ) k_rhs_fast4( const FastArgs a )
+__global__ void __launch_bounds__( 16 * TY, 1 ) k_rhs_fast4( const FastArgs a, const SW4_GRID_CONSTANT FastMaps maps )
 {
    using namespace fast4;
    typedef fast4::Cfg<TY> C;
    constexpr int TX = C::TX, PX = C::PX, PY = C::PY, PLANE = C::PLANE, NT = C::NT;
+#if defined( SW4B200_EMULATE )
    SW4_DYN_SMEM( smem );
+#else
+   extern __shared__ __align__( 128 ) double smem_f4[];
+   double* const smem = smem_f4;
+#endif
    fast4::Ctx<TY> c;
    c.sm = smem;
 
@@ -543,9 +561,8 @@ __global__ void __launch_bounds__( 16 * TY, 1 ) k_rhs_fast4( const FastArgs a )
    fast4::Tm tm;
    if( c.tid == 0 )
    {
-      constexpr int NCP = C::NCP_PLANE + ( EPI != EPI_LU ? C::NCP_OPS : 0 );
-      mbar_init( smem + C::O_MBAR, NCP );
-      mbar_init( smem + C::O_MBAR + 1, NCP );
+      mbar_init( smem + C::O_MBAR, 1 );
+      mbar_init( smem + C::O_MBAR + 1, 1 );
 #if !defined( SW4B200_EMULATE )
       asm volatile( "fence.mbarrier_init.release.cluster;" ::: "memory" );
 #endif
@@ -636,11 +653,11 @@ __global__ void __launch_bounds__( 16 * TY, 1 ) k_rhs_fast4( const FastArgs a )
       ph.par = p & 1;
       ph.wpar = 0;
       ph.t0 = 2 * C::NH * m3; ph.t2 = 2 * C::NH * ( ( m3 + 1 ) % 3 );
-      fast4::stage<TY, EPI>( a, c, p, ph.slot, ph.par );
+      fast4::stage<TY, EPI>( a, maps, c, p, ph.slot, ph.par );
    }
    for( int p = c.ka - 2; p <= plast; p++ )
    {
-      fast4::step<TY, EPI>( a, c, s, tm, p, ph );
+      fast4::step<TY, EPI>( a, maps, c, s, tm, p, ph );
       // next plane
       ph.slot = ph.slot == 5 ? 0 : ph.slot + 1;
 #pragma unroll
@@ -661,6 +678,30 @@ __global__ void __launch_bounds__( 16 * TY, 1 ) k_rhs_fast4( const FastArgs a )
 
 #ifndef SW4B200_EMULATE
 namespace {
+// tensor map of one array of the block: dims (ni, nj, nk), box bx x by x 1, no swizzle, zeros outside the array
+int make_tmap( TMap* m, const double* base, const Block& b, int bx, int by )
+{
+   typedef CUresult ( *Encode )( CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+				 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill );
+   static Encode encode = 0;
+   if( !encode )
+   {
+      void* fn = 0;
+      cudaDriverEntryPointQueryResult qres;
+      if( cudaGetDriverEntryPoint( "cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres ) != cudaSuccess || !fn )
+	 return set_error( "k_rhs_fast4: cuTensorMapEncodeTiled is not available from the driver" );
+      encode = (Encode)fn;
+   }
+   const cuuint64_t dims[3] = { (cuuint64_t)b.ni, (cuuint64_t)b.nj, (cuuint64_t)b.nk };
+   const cuuint64_t strides[2] = { (cuuint64_t)b.ni * 8, (cuuint64_t)b.nij * 8 };
+   const cuuint32_t box[3] = { (cuuint32_t)bx, (cuuint32_t)by, 1 };
+   const cuuint32_t estr[3] = { 1, 1, 1 };
+   const CUresult r = encode( m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+			      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
+   if( r != CUDA_SUCCESS ) return set_error( "k_rhs_fast4: cuTensorMapEncodeTiled failed (%d)", (int)r );
+   return 0;
+}
+
 template <int TY, int EPI>
 int launch_fast4_t( FastArgs a, cudaStream_t st )
 {
@@ -676,10 +717,21 @@ int launch_fast4_t( FastArgs a, cudaStream_t st )
    if( a.kchunk <= 0 ) a.kchunk = fast_kchunk( a.b, a.khi - a.klo + 1, TY );
    if( a.kchunk > C::SZMAX - 6 ) a.kchunk = C::SZMAX - 6;
    const Block& b = a.b;
+   FastMaps maps;
+   memset( &maps, 0, sizeof( maps ) );
+   for( int f = 0; f < 3; f++ )
+      if( make_tmap( &maps.u[f], a.u[f], b, C::PX, C::PY ) ) return 1;
+   if( make_tmap( &maps.mu, a.mu, b, C::PX, C::PY ) || make_tmap( &maps.la, a.la, b, C::PX, C::PY ) ) return 1;
+   if( EPI != EPI_LU )
+   {
+      if( make_tmap( &maps.rho, a.rho, b, C::TX, TY ) ) return 1;
+      for( int f = 0; f < 3; f++ )
+	 if( make_tmap( &maps.um[f], a.um[f], b, C::TX, TY ) ) return 1;
+   }
    dim3 bs( C::NT, 1, 1 );
    dim3 gs( ( b.ni - 4 + C::TX - 1 ) / C::TX, ( b.nj - 4 + TY - 1 ) / TY, ( a.khi - a.klo + 1 + a.kchunk - 1 ) / a.kchunk );
    ProfScope prof( EPI == EPI_PRED ? "rhs_fast_pred" : ( EPI == EPI_CORR ? "rhs_fast_corr" : "rhs_fast_lu" ), st );
-   k_rhs_fast4<TY, EPI><<<gs, bs, smem, st>>>( a );
+   k_rhs_fast4<TY, EPI><<<gs, bs, smem, st>>>( a, maps );
    count_launch();
    return check_launch( "k_rhs_fast4" );
 }

@@ -50,9 +50,12 @@ extern "C" int emu_rhs_fast( int gen, int epi, int ifirst, int ilast, int jfirst
       typedef fast4::Cfg<TY4> C4;
       dim3 bs( C4::NT, 1, 1 );
       dim3 gs( ( a.b.ni - 4 + C4::TX - 1 ) / C4::TX, ( a.b.nj - 4 + TY4 - 1 ) / TY4, ( khi - klo + 1 + kchunk - 1 ) / kchunk );
-      if( epi == EPI_LU ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_LU>( a ); } );
-      else if( epi == EPI_PRED ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_PRED>( a ); } );
-      else emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_CORR>( a ); } );
+      FastMaps maps; // (the emulated TMA tile load reads through the array base)
+      for( int c = 0; c < 3; c++ ) { maps.u[c].base = a.u[c]; maps.um[c].base = a.um[c]; }
+      maps.mu.base = a.mu; maps.la.base = a.la; maps.rho.base = a.rho;
+      if( epi == EPI_LU ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_LU>( a, maps ); } );
+      else if( epi == EPI_PRED ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_PRED>( a, maps ); } );
+      else emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_CORR>( a, maps ); } );
       return 0;
    }
    if( gen >= 3000 )
