@@ -23,7 +23,7 @@
 #include <cstdlib>
 
 #ifndef SW4B200_DEFAULT_FAST_GEN
-#define SW4B200_DEFAULT_FAST_GEN 2
+#define SW4B200_DEFAULT_FAST_GEN 4
 #endif
 
 namespace sw4b200 {
@@ -448,9 +448,10 @@ int launch_fast2( int epi, FastArgs a, cudaStream_t st );
 int launch_fast3( int variant, int epi, const FastArgs& a, cudaStream_t st );
 int launch_fast4( int epi, const FastArgs& a, cudaStream_t st );
 
-// Generation of the interior kernel.  Default: the third generation (rhs4sg_fast3.cu, 32x12 tile, z state in
-// tensor memory).  SW4B200_FAST_GEN=1 / 2 select the earlier generations, 3000+10*TY+TMODE a variant of the third
-// (3122 = default, 3121, 3082, 3081); all are kept for A/B measurements.
+// Generation of the interior kernel.  Default: the fourth generation (rhs4sg_fast4.cu: x-pair register blocking, z state
+// in tensor memory, TMA-staged planes; grids whose rows are not 16-byte aligned fall back to the second generation
+// inside launch_fast4).  SW4B200_FAST_GEN=1 / 2 select the earlier generations, 3000+10*TY+TMODE a variant of the third
+// (3122, 3121, 3082, 3081: one point per thread with the z state in tensor memory); all are kept for A/B measurements.
 static int fast_generation()
 {
    static int v = -1;

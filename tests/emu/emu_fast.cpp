@@ -53,9 +53,9 @@ extern "C" int emu_rhs_fast( int gen, int epi, int ifirst, int ilast, int jfirst
       FastMaps maps; // (the emulated TMA tile load reads through the array base)
       for( int c = 0; c < 3; c++ ) { maps.u[c].base = a.u[c]; maps.um[c].base = a.um[c]; }
       maps.mu.base = a.mu; maps.la.base = a.la; maps.rho.base = a.rho;
-      if( epi == EPI_LU ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_LU>( a, maps ); } );
-      else if( epi == EPI_PRED ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_PRED>( a, maps ); } );
-      else emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_CORR>( a, maps ); } );
+      if( epi == EPI_LU ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_LU, 1>( a, maps ); } );
+      else if( epi == EPI_PRED ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_PRED, 1>( a, maps ); } );
+      else emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_CORR, 1>( a, maps ); } );
       return 0;
    }
    if( gen >= 3000 )
