@@ -307,14 +307,16 @@ def main_ours(a):
         dur = prof["rhs_fast_pred"]["ms_per_step"] / prof["rhs_fast_pred"]["launches_per_step"]
         ach = per_launch_bytes / (dur * 1e-3) / 1e9
         # DRAM traffic of that kernel from the committed ncu --set full capture (bytes per point, scaled to this launch)
-        traffic, traffic_src = None, None
+        traffic, traffic_src, kname = None, None, "k_rhs_fast4<16,EPI_PRED> (fused rhs4sg + predictor + acceleration)"
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01b_traffic.json")))
-            traffic = tr["k_rhs_fast2<8,EPI_PRED>"]["dram_bytes_per_point"] * a.nx * a.ny * rows / prof["rhs_fast_pred"]["launches_per_step"]
-            traffic_src = "profiles/r01b_traffic.json (ncu dram__bytes_read+write per point of the same kernel, scaled to this launch)"
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01d_traffic.json")))
+            ent = tr["pred"]
+            kname = ent.get("kernel", kname)
+            traffic = ent["dram_bytes_per_point"] * a.nx * a.ny * rows / prof["rhs_fast_pred"]["launches_per_step"]
+            traffic_src = "profiles/r01d_traffic.json (ncu dram__bytes_read+write per point of the same kernel, scaled to this launch)"
         except Exception:
             pass
-        roof = {"bound": "hbm", "kernel": "k_rhs_fast2<8,EPI_PRED> (fused rhs4sg + predictor + acceleration)",
+        roof = {"bound": "hbm", "kernel": kname,
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_unit": "bytes per launch",
                 "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_point": BYTES_PASS_A, "points_per_launch": a.nx * a.ny * rows,

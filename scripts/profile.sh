@@ -4,5 +4,5 @@ TAG=${1:-r01}
 mkdir -p gpurun_out
 B="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --nx 768 --ny 768 --nzl 96"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $B > gpurun_out/launches_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_rhs_fast2 -s 2 -c 2 -f -o gpurun_out/prof_fast_$TAG $B > gpurun_out/prof_fast_$TAG.log 2>&1
-ls -la gpurun_out/
+ncu --set full --clock-control none --import-source on -k regex:k_rhs_fast4 -s 2 -c 2 -f -o gpurun_out/prof_fast_$TAG $B > gpurun_out/prof_fast_$TAG.log 2>&1
+ls -la gpurun_out/ | tail -5
