@@ -297,18 +297,21 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
 	    if( m == 0 ) r_ = s.rp[0][t] + ( a.cof144 * sxo[t] ) * ( xd[t] + syo * yd[t] );
 	    else if( m == 1 ) r_ = s.rp[1][t] + ( a.cof144 * syo ) * ( sxo[t] * xd[t] + yd[t] );
 	    else r_ = s.rp[2][t] + a.cof144 * ( sxo[t] * xd[t] + syo * yd[t] );
+	    // (dense forcing and a predictor without the acceleration output take the cp.async kernel: launch_fast4)
+	    double o1, o2 = 0;
+	    if( EPI == EPI_LU )
+	       o1 = r_;
+	    else if( EPI == EPI_PRED )
+	    {
+	       o1 = 2 * ring[m][t] - pick( e_um, t ) + fr[t] * r_;
+	       o2 = r_ * rinv[t];
+	    }
+	    else
+	       o1 = pick( e_um, t ) + fr[t] * r_;
 	    if( fin[t] )
 	    {
-	       if( EPI != EPI_LU && a.fo[0] ) r_ += a.fo[m][qf + t];
-	       if( EPI == EPI_LU )
-		  a.out[m][qf + t] = r_;
-	       else if( EPI == EPI_PRED )
-	       {
-		  a.out[m][qf + t] = 2 * ring[m][t] - pick( e_um, t ) + fr[t] * r_;
-		  if( a.out2[0] ) a.out2[m][qf + t] = r_ * rinv[t];
-	       }
-	       else
-		  a.out[m][qf + t] = pick( e_um, t ) + fr[t] * r_;
+	       a.out[m][qf + t] = o1;
+	       if( EPI == EPI_PRED ) a.out2[m][qf + t] = o2;
 	    }
 	 }
       }
@@ -756,6 +759,10 @@ int launch_fast4( int epi, const FastArgs& a, cudaStream_t st )
    uintptr_t al = (uintptr_t)a.u[0] | (uintptr_t)a.u[1] | (uintptr_t)a.u[2] | (uintptr_t)a.mu | (uintptr_t)a.la;
    if( epi != EPI_LU ) al |= (uintptr_t)a.rho | (uintptr_t)a.um[0] | (uintptr_t)a.um[1] | (uintptr_t)a.um[2];
    if( ( a.b.ni & 1 ) || ( al & 15 ) ) return launch_fast2( epi, a, st );
+   // dense forcing arrays and a predictor without the stored acceleration are not on the time-stepping path (forcing is
+   // injected sparsely, pass A always stores uacc): the operator-level calls that use them take the cp.async kernel too
+   if( epi != EPI_LU && a.fo[0] ) return launch_fast2( epi, a, st );
+   if( epi == EPI_PRED && !a.out2[0] ) return launch_fast2( epi, a, st );
    // SW4B200_F4_STAGGER=1: warps 0-3 run the phases of a step in another order than warps 4-7 (finish first), so that
    // the two warps of a scheduler are in different phases.  Measured on B200: 19.9 ms against 19.0 ms per predictor
    // pass -- off by default, kept for A/B runs.

@@ -99,12 +99,14 @@ def test_emu_predictor_and_corrector_epilogues(emu):
     box = Box(*even((41, 19, 15)))
     f = random_fields(box, seed=23)
     h, dt = 0.4, 0.05
+    if GEN == 4:      # dense forcing is not on the fourth generation's path (launch_fast4 sends it to the second)
+        f["fo"] = np.zeros_like(f["fo"])
     O = oracle()
     lu = cpu_lu(box, f, h)
     up = np.zeros(3 * box.npts)
     O.predfort(1, box.bounds, up, f["u"], f["um"], lu, f["fo"], f["rho"], dt * dt)
     out = np.zeros(3 * box.npts); out2 = np.zeros(3 * box.npts)
-    run(emu, 1, box, box.kfirst + 2, box.klast - 2, 6, f, 1 / h ** 2, out, out2=out2, um=f["um"], rho=f["rho"], fo=f["fo"], fac=dt * dt)
+    run(emu, 1, box, box.kfirst + 2, box.klast - 2, 6, f, 1 / h ** 2, out, out2=out2, um=f["um"], rho=f["rho"], fo=None if GEN == 4 else f["fo"], fac=dt * dt)
     inner = (slice(None), slice(2, -2), slice(2, -2), slice(2, -2))
     r4 = lambda x: x.reshape(3, box.nk, box.nj, box.ni)
     assert relerr(r4(out)[inner], r4(up)[inner]) < 1e-13
@@ -114,5 +116,5 @@ def test_emu_predictor_and_corrector_epilogues(emu):
     ref = f["up"].copy()
     O.corrfort(1, box.bounds, ref, lu, f["fo"], f["rho"], dt ** 4)
     out = f["up"].copy()
-    run(emu, 2, box, box.kfirst + 2, box.klast - 2, 6, f, 1 / h ** 2, out, um=out, rho=f["rho"], fo=f["fo"], fac=dt ** 4 / 12)
+    run(emu, 2, box, box.kfirst + 2, box.klast - 2, 6, f, 1 / h ** 2, out, um=out, rho=f["rho"], fo=None if GEN == 4 else f["fo"], fac=dt ** 4 / 12)
     assert relerr(r4(out)[inner], r4(ref)[inner]) < 1e-13
