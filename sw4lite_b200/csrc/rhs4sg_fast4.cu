@@ -49,6 +49,13 @@ struct FastMaps
    TMap rho, um[3];   // boxes TX x TY x 1 (own points)
 };
 
+#if defined( SW4B200_EMULATE )
+#define F4SM( c ) ( ( c ).sm )
+#else
+extern __shared__ __align__( 128 ) double smem_f4[];
+#define F4SM( c ) smem_f4
+#endif
+
 namespace fast4 {
 
 using fast::W4;
@@ -165,7 +172,7 @@ template <int TY>
 struct Ctx
 {
    typedef Cfg<TY> C;
-   double* sm;
+   double* sm; // (device code addresses the shared array by name, F4SM: no generic-to-shared conversions)
    int p0;
    int li0, lj0; // local (array) index of the tile's first output
    int tid, txh, ty, o;
@@ -196,7 +203,7 @@ __device__ __forceinline__ void stage( const FastArgs& a, const FastMaps& maps, 
    typedef Cfg<TY> C;
    if( p > c.pend + 1 || c.tid != 0 ) return;
    const Block& b = a.b;
-   double* const mbar = c.sm + C::O_MBAR + par;
+   double* const mbar = F4SM( c ) + C::O_MBAR + par;
    const int kq = p - 3;
    const bool plane = p <= c.pend; // (the step after the last plane only finishes plane kb)
    const bool ops = EPI != EPI_LU && kq >= c.ka && kq <= c.kb;
@@ -206,13 +213,13 @@ __device__ __forceinline__ void stage( const FastArgs& a, const FastMaps& maps, 
       const int c0 = c.li0 - 2, c1 = c.lj0 - 2, c2 = p - b.kfirst;
 #pragma unroll
       for( int f = 0; f < 3; f++ )
-	 tma_tile<C::PX, C::PY>( c.sm + C::O_UVW + ( f * C::NSLOT + slot ) * C::PLANE, &maps.u[f], b, c0, c1, c2, mbar );
-      tma_tile<C::PX, C::PY>( c.sm + C::O_ML + ( 0 * 2 + par ) * C::PLANE, &maps.mu, b, c0, c1, c2, mbar );
-      tma_tile<C::PX, C::PY>( c.sm + C::O_ML + ( 1 * 2 + par ) * C::PLANE, &maps.la, b, c0, c1, c2, mbar );
+	 tma_tile<C::PX, C::PY>( F4SM( c ) + C::O_UVW + ( f * C::NSLOT + slot ) * C::PLANE, &maps.u[f], b, c0, c1, c2, mbar );
+      tma_tile<C::PX, C::PY>( F4SM( c ) + C::O_ML + ( 0 * 2 + par ) * C::PLANE, &maps.mu, b, c0, c1, c2, mbar );
+      tma_tile<C::PX, C::PY>( F4SM( c ) + C::O_ML + ( 1 * 2 + par ) * C::PLANE, &maps.la, b, c0, c1, c2, mbar );
    }
    if( ops )
    {
-      double* const d = c.sm + C::O_OP + par * C::OPS;
+      double* const d = F4SM( c ) + C::O_OP + par * C::OPS;
       tma_tile<C::TX, TY>( d, &maps.rho, b, c.li0, c.lj0, kq - b.kfirst, mbar );
 #pragma unroll
       for( int m = 0; m < 3; m++ ) tma_tile<C::TX, TY>( d + ( m + 1 ) * C::TX * TY, &maps.um[m], b, c.li0, c.lj0, kq - b.kfirst, mbar );
@@ -235,7 +242,7 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
    const Block& b = a.b;
    const int k = p - 2, kf = p - 3;
 
-   mbar_wait( c.sm + C::O_MBAR + ph.par, ( ph.wpar >> ph.par ) & 1 ); // the rows of plane p have landed
+   mbar_wait( F4SM( c ) + C::O_MBAR + ph.par, ( ph.wpar >> ph.par ) & 1 ); // the rows of plane p have landed
    __syncthreads(); // the E products of plane k-1 are visible; slot of plane p-5 is free
    stage<TY, EPI>( a, maps, c, p + 1, ph.slot == NSLOT - 1 ? 0 : ph.slot + 1, ph.par ^ 1 );
    tm.wait_st(); // the records stored by the earlier steps (long done) are readable
@@ -247,19 +254,19 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
    // strx at i-2..i+3 (i = left point), stry at j-2..j+2: re-read every step instead of held in 22 registers
    double csx[6], csy[5];
    {
-      const D2 s0 = ld2( c.sm + C::O_SX + 2 * c.txh ), s1 = ld2( c.sm + C::O_SX + 2 * c.txh + 2 ), s2 = ld2( c.sm + C::O_SX + 2 * c.txh + 4 );
+      const D2 s0 = ld2( F4SM( c ) + C::O_SX + 2 * c.txh ), s1 = ld2( F4SM( c ) + C::O_SX + 2 * c.txh + 2 ), s2 = ld2( F4SM( c ) + C::O_SX + 2 * c.txh + 4 );
       csx[0] = s0.x; csx[1] = s0.y; csx[2] = s1.x; csx[3] = s1.y; csx[4] = s2.x; csx[5] = s2.y;
 #pragma unroll
-      for( int j = 0; j < 5; j++ ) csy[j] = c.sm[C::O_SY + c.ty + j];
+      for( int j = 0; j < 5; j++ ) csy[j] = F4SM( c )[C::O_SY + c.ty + j];
    }
    const double syo = csy[2];
    const double sxo[2] = { csx[2], csx[3] };
    // ---- finish plane kf = k-1: difference its exchanged products (published by this step's barrier), one component
    // at a time (7 pair loads in flight)
    auto finish = [&]() {
-      const double* const ex = c.sm + C::O_EX + EF * C::EX + c.ty * PX + 2 * c.txh + 2;
-      const double* const ey = c.sm + C::O_EY + EF * C::EY + ( c.ty + 2 ) * TX + 2 * c.txh;
-      const double* const d = c.sm + C::O_OP + ph.par * C::OPS + 2 * c.tid;
+      const double* const ex = F4SM( c ) + C::O_EX + EF * C::EX + c.ty * PX + 2 * c.txh + 2;
+      const double* const ey = F4SM( c ) + C::O_EY + EF * C::EY + ( c.ty + 2 ) * TX + 2 * c.txh;
+      const double* const d = F4SM( c ) + C::O_OP + ph.par * C::OPS + 2 * c.tid;
       double fr[2] = { 0, 0 }, rinv[2] = { 0, 0 }; // PRED: dt^2/rho, 1/rho ; CORR: dt^4/(12 rho)
       if( EPI != EPI_LU )
       {
@@ -290,6 +297,7 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
 	 D2 e_um;
 	 e_um.x = e_um.y = 0;
 	 if( EPI != EPI_LU ) e_um = ld2( d + ( m + 1 ) * TX * TY );
+	 double o1[2], o2[2] = { 0, 0 };
 #pragma unroll
 	 for( int t = 0; t < 2; t++ )
 	 {
@@ -298,21 +306,27 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
 	    else if( m == 1 ) r_ = s.rp[1][t] + ( a.cof144 * syo ) * ( sxo[t] * xd[t] + yd[t] );
 	    else r_ = s.rp[2][t] + a.cof144 * ( sxo[t] * xd[t] + syo * yd[t] );
 	    // (dense forcing and a predictor without the acceleration output take the cp.async kernel: launch_fast4)
-	    double o1, o2 = 0;
 	    if( EPI == EPI_LU )
-	       o1 = r_;
+	       o1[t] = r_;
 	    else if( EPI == EPI_PRED )
 	    {
-	       o1 = 2 * ring[m][t] - pick( e_um, t ) + fr[t] * r_;
-	       o2 = r_ * rinv[t];
+	       o1[t] = 2 * ring[m][t] - pick( e_um, t ) + fr[t] * r_;
+	       o2[t] = r_ * rinv[t];
 	    }
 	    else
-	       o1 = pick( e_um, t ) + fr[t] * r_;
-	    if( fin[t] )
-	    {
-	       a.out[m][qf + t] = o1;
-	       if( EPI == EPI_PRED ) a.out2[m][qf + t] = o2;
-	    }
+	       o1[t] = pick( e_um, t ) + fr[t] * r_;
+	 }
+	 // the pair is 16-byte aligned in global memory too (even ni, even li): one store per array unless the right
+	 // point is outside the interior
+	 if( fin[1] )
+	 {
+	    st2( a.out[m] + qf, o1[0], o1[1] );
+	    if( EPI == EPI_PRED ) st2( a.out2[m] + qf, o2[0], o2[1] );
+	 }
+	 else if( fin[0] )
+	 {
+	    a.out[m][qf] = o1[0];
+	    if( EPI == EPI_PRED ) a.out2[m][qf] = o2[0];
 	 }
       }
    };
@@ -321,7 +335,7 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
    // ---- in-plane pieces of plane p: an x pass and a y pass over the fields, so that only the weights of one
    // direction (2 points x 2 coefficient sets) are live next to the neighbours of one field
    {
-      double* const sm = c.sm;
+      double* const sm = F4SM( c );
       const double* const pf[3] = { sm + C::O_UVW + 0 * NSLOT * PLANE + ph.o[0] + c.o, sm + C::O_UVW + 1 * NSLOT * PLANE + ph.o[0] + c.o,
 				    sm + C::O_UVW + 2 * NSLOT * PLANE + ph.o[0] + c.o };
       const double* const pm = sm + C::O_ML + ( 0 * 2 + ML ) * PLANE + c.o;
@@ -430,14 +444,14 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
    tm.template ld<16, 8>( tq + 2, ph.c[2] );	 // pr1 pr2 e1 e2
    tm.template ld<32, 4>( tq + 10, ph.c[2] ); // e4 e5
 
-   const double szk = k >= c.p0 ? c.sm[C::O_SZ + k - c.p0] : 0.0;
+   const double szk = k >= c.p0 ? F4SM( c )[C::O_SZ + k - c.p0] : 0.0;
    auto helper = [&]() {
       // ring of width 2 around the tile: the same products recomputed from the staged planes
       // (plane k sits in slot R2, k-2..k+2 in R4..R0); mu, la of the ring points from the side copy
       for( int hh = c.tid; hh < NH; hh += NT )
       {
-	 const double* const sf = c.sm + C::O_UVW;
-	 double* const hml = c.sm + C::O_HML;
+	 const double* const sf = F4SM( c ) + C::O_UVW;
+	 double* const hml = F4SM( c ) + C::O_HML;
 	 int sx_, sy_;
 	 if( hh < 4 * TY )
 	 {
@@ -451,8 +465,8 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
 	    sy_ = hy < 2 ? hy : TY + hy; sx_ = col + 2;
 	 }
 	 const int oo = sy_ * PX + sx_;
-	 hml[ph.t0 + hh] = c.sm[C::O_ML + ( 0 * 2 + ML ) * PLANE + oo];
-	 hml[ph.t0 + NH + hh] = c.sm[C::O_ML + ( 1 * 2 + ML ) * PLANE + oo];
+	 hml[ph.t0 + hh] = F4SM( c )[C::O_ML + ( 0 * 2 + ML ) * PLANE + oo];
+	 hml[ph.t0 + NH + hh] = F4SM( c )[C::O_ML + ( 1 * 2 + ML ) * PLANE + oo];
 	 const double hm = hml[ph.t2 + hh], hl = hml[ph.t2 + NH + hh];
 	 const double* const qu = sf + 0 * NSLOT * PLANE + ph.o[2] + oo;
 	 const double* const qv = sf + 1 * NSLOT * PLANE + ph.o[2] + oo;
@@ -464,8 +478,8 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
 	    const double hdyu = d0u( qu[-2 * PX], qu[-PX], qu[PX], qu[2 * PX] );
 	    const double hdzu = d0u( sf[0 * NSLOT * PLANE + ph.o[4] + oo], sf[0 * NSLOT * PLANE + ph.o[3] + oo],
 				     sf[0 * NSLOT * PLANE + ph.o[1] + oo], sf[0 * NSLOT * PLANE + ph.o[0] + oo] );
-	    double* const hx_ = c.sm + C::O_EX + EB * C::EX + ( sy_ - 2 ) * PX + sx_;
-	    hx_[0] = hl * ( c.sm[C::O_SY + sy_] * hdyv + szk * hdzw );
+	    double* const hx_ = F4SM( c ) + C::O_EX + EB * C::EX + ( sy_ - 2 ) * PX + sx_;
+	    hx_[0] = hl * ( F4SM( c )[C::O_SY + sy_] * hdyv + szk * hdzw );
 	    hx_[TY * PX] = hm * hdyu;
 	    hx_[2 * TY * PX] = ( hm * szk ) * hdzu;
 	 }
@@ -475,9 +489,9 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
 	    const double hdxu = d0u( qu[-2], qu[-1], qu[1], qu[2] );
 	    const double hdzv = d0u( sf[1 * NSLOT * PLANE + ph.o[4] + oo], sf[1 * NSLOT * PLANE + ph.o[3] + oo],
 				     sf[1 * NSLOT * PLANE + ph.o[1] + oo], sf[1 * NSLOT * PLANE + ph.o[0] + oo] );
-	    double* const hy_ = c.sm + C::O_EY + EB * C::EY + sy_ * TX + ( sx_ - 2 );
+	    double* const hy_ = F4SM( c ) + C::O_EY + EB * C::EY + sy_ * TX + ( sx_ - 2 );
 	    hy_[0] = hm * hdxv;
-	    hy_[PY * TX] = hl * ( c.sm[C::O_SX + sx_] * hdxu + szk * hdzw );
+	    hy_[PY * TX] = hl * ( F4SM( c )[C::O_SX + sx_] * hdxu + szk * hdzw );
 	    hy_[2 * PY * TX] = ( hm * szk ) * hdzv;
 	 }
       }
@@ -524,8 +538,8 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
 	 rnew[1][t] = a.cof6 * rz1 + ( c144z * syo ) * t2[t];
 	 rnew[2][t] = a.cof6 * rz2 + c144z * t3[t];
       }
-      double* const ex = c.sm + C::O_EX + EB * C::EX + c.ty * PX + 2 * c.txh + 2;
-      double* const ey = c.sm + C::O_EY + EB * C::EY + ( c.ty + 2 ) * TX + 2 * c.txh;
+      double* const ex = F4SM( c ) + C::O_EX + EB * C::EX + c.ty * PX + 2 * c.txh + 2;
+      double* const ey = F4SM( c ) + C::O_EY + EB * C::EY + ( c.ty + 2 ) * TX + 2 * c.txh;
       st2( ex, e1[0], e1[1] );
       st2( ex + TY * PX, e2[0], e2[1] );
       st2( ex + 2 * TY * PX, e3[0], e3[1] );
@@ -551,7 +565,6 @@ __global__ void __launch_bounds__( 16 * TY, 1 ) k_rhs_fast4( const FastArgs a, c
 #if defined( SW4B200_EMULATE )
    SW4_DYN_SMEM( smem );
 #else
-   extern __shared__ __align__( 128 ) double smem_f4[];
    double* const smem = smem_f4;
 #endif
    fast4::Ctx<TY> c;
@@ -758,6 +771,8 @@ int launch_fast4( int epi, const FastArgs& a, cudaStream_t st )
    // ni (205, 305, 605 + 4 ghost points ...): those grids take the cp.async kernel of the second generation.
    uintptr_t al = (uintptr_t)a.u[0] | (uintptr_t)a.u[1] | (uintptr_t)a.u[2] | (uintptr_t)a.mu | (uintptr_t)a.la;
    if( epi != EPI_LU ) al |= (uintptr_t)a.rho | (uintptr_t)a.um[0] | (uintptr_t)a.um[1] | (uintptr_t)a.um[2];
+   al |= (uintptr_t)a.out[0] | (uintptr_t)a.out[1] | (uintptr_t)a.out[2];
+   if( epi == EPI_PRED && a.out2[0] ) al |= (uintptr_t)a.out2[0] | (uintptr_t)a.out2[1] | (uintptr_t)a.out2[2];
    if( ( a.b.ni & 1 ) || ( al & 15 ) ) return launch_fast2( epi, a, st );
    // dense forcing arrays and a predictor without the stored acceleration are not on the time-stepping path (forcing is
    // injected sparsely, pass A always stores uacc): the operator-level calls that use them take the cp.async kernel too
