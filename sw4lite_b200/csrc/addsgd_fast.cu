@@ -139,7 +139,78 @@ __global__ void __launch_bounds__( SG_TX* SG_TY ) k_addsgd4_fast( Block b, Int6 
    }
 }
 
+// Boxes in which only dcz is non-zero (the bottom layer away from the x/y layers: most of the damping points of a
+// production grid).  The x and y terms of addsgd4fort_indrev are exactly zero there, so the update reduces to the z term:
+// no neighbours in the plane, hence no shared memory and no barriers -- a pure streaming march down the z columns
+// (104 B per point).  Same arithmetic as k_addsgd4_fast for its z term, so the two kernels agree bit for bit where
+// both apply.
+__global__ void __launch_bounds__( 256 ) k_addsgd4_zonly( Block b, Int6 box, int kchunk, double* __restrict__ up, const double* __restrict__ u,
+							    const double* __restrict__ um, const double* __restrict__ rho,
+							    const double* __restrict__ dcz, const double* __restrict__ strz,
+							    const double* __restrict__ cox, const double* __restrict__ coy, double beta )
+{
+   const int li = box.v[0] + blockIdx.x * 32 + threadIdx.x, lj = box.v[2] + blockIdx.y * 8 + threadIdx.y;
+   const int ka = box.v[4] + blockIdx.z * kchunk;
+   const int kb = ka + kchunk - 1 < box.v[5] ? ka + kchunk - 1 : box.v[5];
+   if( ka > kb || li > box.v[1] || lj > box.v[3] ) return;
+   const long long own = (long long)lj * b.ni + li;
+   const double cxi = cox[li], cyj = coy[lj];
+   double d[3][5], rh[3];
+#pragma unroll
+   for( int c = 0; c < 3; c++ )
+   {
+      d[c][0] = 0;
+#pragma unroll
+      for( int m = 1; m < 5; m++ )
+      {
+	 const long long q = b.nij * ( ka - 3 + m ) + own;
+	 d[c][m] = u[c * b.npts + q] - um[c * b.npts + q];
+      }
+   }
+   rh[0] = 0; rh[1] = rho[b.nij * ( ka - 1 ) + own]; rh[2] = rho[b.nij * ka + own];
+   for( int k = ka; k <= kb; k++ )
+   {
+#pragma unroll
+      for( int c = 0; c < 3; c++ )
+#pragma unroll
+	 for( int m = 0; m < 4; m++ ) d[c][m] = d[c][m + 1];
+      rh[0] = rh[1]; rh[1] = rh[2];
+      const long long q = b.nij * k + own, q2 = q + 2 * b.nij;
+#pragma unroll
+      for( int c = 0; c < 3; c++ ) d[c][4] = u[c * b.npts + q2] - um[c * b.npts + q2];
+      rh[2] = rho[q + b.nij];
+      const double prez = strz[k] * cxi * cyj; // as k_addsgd4_fast forms it
+      const double birho = beta / rh[1];
+      const double czm = dcz[k - 1], cz0 = dcz[k], czp = dcz[k + 1];
+#pragma unroll
+      for( int c = 0; c < 3; c++ )
+      {
+	 const double s = prez * sg_term( d[c][0], d[c][1], d[c][2], d[c][3], d[c][4], rh[0], rh[1], rh[2], czm, cz0, czp );
+	 up[c * b.npts + q] = up[c * b.npts + q] - birho * s;
+      }
+   }
+}
+
 } // namespace
+
+int launch_addsgd4_zonly( const Block& b, const Int6& box, double* up, const double* u, const double* um, const double* rho,
+			  const double* dcz, const double* strz, const double* cox, const double* coy, double beta, cudaStream_t st )
+{
+   const int nx = box.v[1] - box.v[0] + 1, ny = box.v[3] - box.v[2] + 1, nz = box.v[5] - box.v[4] + 1;
+   if( beta == 0 || nx <= 0 || ny <= 0 || nz <= 0 ) return 0;
+   ProfScope prof( "addsgd", st );
+   const long long tiles = (long long)( ( nx + 31 ) / 32 ) * ( ( ny + 7 ) / 8 );
+   long long nch = ( 148LL * 32 + tiles - 1 ) / tiles;
+   if( nch < 1 ) nch = 1;
+   int kchunk = (int)( ( nz + nch - 1 ) / nch );
+   if( kchunk < 16 ) kchunk = 16; // (every chunk re-reads 4 planes of u, um)
+   if( kchunk > nz ) kchunk = nz;
+   dim3 bs( 32, 8, 1 );
+   dim3 gs( ( nx + 31 ) / 32, ( ny + 7 ) / 8, ( nz + kchunk - 1 ) / kchunk );
+   k_addsgd4_zonly<<<gs, bs, 0, st>>>( b, box, kchunk, up, u, um, rho, dcz, strz, cox, coy, beta );
+   count_launch();
+   return check_launch( "k_addsgd4_zonly" );
+}
 
 int launch_addsgd4_fast( const Block& b, const Int6& box, double* up, const double* u, const double* um,
 			 const double* rho, const double* dcx, const double* dcy, const double* dcz, const double* strx,

@@ -242,6 +242,7 @@ struct sw4b200_grid
    bool fast;		       // SoA Cartesian throughput path
    std::vector<double>* h_dc[3]; // host copies of the damping arrays -> boxes where the damping is non-zero
    std::vector<Int6>* sgd_boxes;
+   std::vector<int>* sgd_zonly; // per box: only dcz is non-zero in it (streaming z-only kernel)
    bool sgd_boxes_valid;
    // device-resident source amplitude tables and receiver records for sw4b200_grid_run
    int series_steps;
@@ -636,6 +637,7 @@ sw4b200_grid* sw4b200_grid_create( const sw4b200_grid_desc* desc )
    g->fast = desc->corder == 1 && !desc->curvilinear && use_fast_path();
    for( int d = 0; d < 3; d++ ) g->h_dc[d] = new std::vector<double>();
    g->sgd_boxes = new std::vector<Int6>();
+   g->sgd_zonly = new std::vector<int>();
    double** three[4] = { &g->U, &g->Um, &g->Up, &g->Uacc };
    for( int a = 0; a < 4; a++ )
    {
@@ -695,6 +697,7 @@ int sw4b200_grid_destroy( sw4b200_grid* g )
 		      g->halo_buf[0], g->halo_buf[1], g->d_fser, g->d_fttser, g->d_recser, g->Lu };
    for( int d = 0; d < 3; d++ ) delete g->h_dc[d];
    delete g->sgd_boxes;
+   delete g->sgd_zonly;
    for( double* p : ptrs ) if( p ) cudaFree( p );
    for( int d = 0; d < 3; d++ ) { cudaFree( g->str[d] ); cudaFree( g->dc[d] ); cudaFree( g->co[d] ); }
    for( int s = 0; s < 6; s++ ) if( g->bforce[s] ) cudaFree( g->bforce[s] );
@@ -904,16 +907,28 @@ static void build_sgd_boxes( sw4b200_grid* g )
       }
    }
    const std::pair<int, int> fx( w, n[0] - 1 - w ), fy( w, n[1] - 1 - w );
-   auto add = [&]( std::pair<int, int> x, std::pair<int, int> y, std::pair<int, int> z ) {
+   g->sgd_zonly->clear();
+   auto add = [&]( std::pair<int, int> x, std::pair<int, int> y, std::pair<int, int> z, int zonly ) {
       Int6 b = { { x.first, x.second, y.first, y.second, z.first, z.second } };
       g->sgd_boxes->push_back( b );
+      g->sgd_zonly->push_back( zonly );
    };
-   for( auto& z : on[2] ) add( fx, fy, z );
+   // z-active planes: the columns away from the x and y layers only see dcz (most of a production grid's damping
+   // points: the bottom layer) and take the streaming kernel; the x / y layers inside them the general one
+   for( auto& z : on[2] )
+   {
+      for( auto& y : on[1] ) add( fx, y, z, 0 );
+      for( auto& y : off[1] )
+      {
+	 for( auto& x : on[0] ) add( x, y, z, 0 );
+	 for( auto& x : off[0] ) add( x, y, z, order == 4 ? 1 : 0 );
+      }
+   }
    for( auto& z : off[2] )
    {
-      for( auto& y : on[1] ) add( fx, y, z );
+      for( auto& y : on[1] ) add( fx, y, z, 0 );
       for( auto& y : off[1] )
-	 for( auto& x : on[0] ) add( x, y, z );
+	 for( auto& x : on[0] ) add( x, y, z, 0 );
    }
    g->sgd_boxes_valid = true;
 }
@@ -925,15 +940,20 @@ static int damping_dev( sw4b200_grid* g, int part )
    int r[2][2];
    const int n = part_ranges( g, part, r );
    for( int m = 0; m < n; m++ )
-      for( const Int6& box0 : *g->sgd_boxes )
+      for( size_t ib = 0; ib < g->sgd_boxes->size(); ib++ )
       {
-	 Int6 box = box0;
+	 Int6 box = ( *g->sgd_boxes )[ib];
 	 const int ka = r[m][0] - g->b.kfirst, kb = r[m][1] - g->b.kfirst;
 	 if( box.v[4] < ka ) box.v[4] = ka;
 	 if( box.v[5] > kb ) box.v[5] = kb;
 	 if( box.v[5] < box.v[4] ) continue;
-	 if( launch_addsgd_box( g->d.sg_order, g->b, box, g->Up, g->U, g->Um, g->rho, g->dc[0], g->dc[1], g->dc[2],
-				g->str[0], g->str[1], g->str[2], g->co[0], g->co[1], g->co[2], g->d.beta, g->st ) )
+	 if( ( *g->sgd_zonly )[ib] && g->d.corder == 1 )
+	 {
+	    if( launch_addsgd4_zonly( g->b, box, g->Up, g->U, g->Um, g->rho, g->dc[2], g->str[2], g->co[0], g->co[1], g->d.beta, g->st ) )
+	       return 1;
+	 }
+	 else if( launch_addsgd_box( g->d.sg_order, g->b, box, g->Up, g->U, g->Um, g->rho, g->dc[0], g->dc[1], g->dc[2],
+				     g->str[0], g->str[1], g->str[2], g->co[0], g->co[1], g->co[2], g->d.beta, g->st ) )
 	    return 1;
       }
    return 0;

@@ -109,6 +109,8 @@ int launch_addsgd4_fast( const Block& b, const Int6& box, double* up, const doub
 			 const double* rho, const double* dcx, const double* dcy, const double* dcz, const double* strx,
 			 const double* stry, const double* strz, const double* cox, const double* coy, const double* coz,
 			 double beta, cudaStream_t st );
+int launch_addsgd4_zonly( const Block& b, const Int6& box, double* up, const double* u, const double* um, const double* rho,
+			  const double* dcz, const double* strz, const double* cox, const double* coy, double beta, cudaStream_t st );
 int launch_bcfortsg( const Block& b, const Int36& wind, int nx, int ny, int nz, double* u, double h,
 		     const Int6& bccnd, const double* mu, const double* la, const Ptr6& bforce,
 		     const double* strx, const double* stry, cudaStream_t st );
