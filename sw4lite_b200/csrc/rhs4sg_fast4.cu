@@ -158,13 +158,15 @@ struct Cfg
    static_assert( ( PLANE % 2 ) == 0 && ( EX % 2 ) == 0 && ( EY % 2 ) == 0 && ( NH % 2 ) == 0 && ( ( PX + PY ) % 2 ) == 0, "16-byte alignment" );
 };
 
-// per-thread register state ([..][2]: the two points): five-plane shift registers, [4] = plane p ... [0] = plane p-4.
-// The march is ONE step body executed for every plane (the rings of the earlier generations needed a step copy per
-// ring position, 6 x 1600 instructions: more than the instruction cache holds); the 40 register moves per step
-// go to the integer pipes, which idle next to the fp64 pipe.
+// per-thread register state ([..][2]: the two points): five-plane shift registers in arrays of six.  The march has TWO
+// step bodies: planes with even k use positions [4]..[0] for planes p..p-4, planes with odd k [5]..[1], and the
+// registers are shifted by two after the odd one: 20 double moves per step instead of 40.  (The rings of the earlier
+// generations needed a step copy per ring position, 6 x 1600 instructions: more than the instruction cache holds.)
+// A plane is always handled by the body of its parity, so z-slab runs execute the undivided run's instruction
+// sequence for every plane and stay bit-identical to it.
 struct State
 {
-   double cu[5][2], cv[5][2], cw[5][2], amz[5][2], alz[5][2];
+   double cu[6][2], cv[6][2], cw[6][2], amz[6][2], alz[6][2];
    double rp[3][2]; // result of the previous plane, still lacking the exchanged cross terms
 };
 
@@ -231,13 +233,13 @@ __device__ __forceinline__ double pick( const D2& v, int t ) { return t ? v.y : 
 // One step of the march: plane p has been staged into ring slot S.  Does the in-plane work of plane p,
 // the z work of plane k=p-2 (publishing its exchanged products in E buffer S&1) and finishes plane k-1
 // (reading E buffer (S+1)&1).
-template <int TY, int EPI, int ORDER>
+template <int TY, int EPI, int ORDER, int H>
 __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, Ctx<TY>& c, State& s, Tm& tm, const int p, const Ph& ph )
 {
    typedef Cfg<TY> C;
    constexpr int TX = C::TX, PX = C::PX, PY = C::PY, PLANE = C::PLANE, NT = C::NT, NSLOT = C::NSLOT, NH = C::NH;
    // shift-register positions of planes p, p-1, ..., p-4
-   constexpr int R0 = 4, R1 = 3, R2 = 2, R3 = 1, R4 = 0;
+   constexpr int R0 = 4 + H, R1 = 3 + H, R2 = 2 + H, R3 = 1 + H, R4 = H;
    const int EB = ph.par, EF = ph.par ^ 1, ML = ph.par;
    const Block& b = a.b;
    const int k = p - 2, kf = p - 3;
@@ -284,7 +286,7 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
 	       fr[t] = a.fac / rh;
 	 }
       }
-      constexpr int RF = ORDER == 1 ? R3 + 1 : R3; // plane kf = p-3 (ORDER 1 runs before this step's shift)
+      constexpr int RF = R3; // plane kf = p-3
       const double* const ring[3] = { &s.cu[RF][0], &s.cv[RF][0], &s.cw[RF][0] };
 #pragma unroll
       for( int m = 0; m < 3; m++ )
@@ -377,12 +379,6 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
 #pragma unroll
       for( int t = 0; t < 2; t++ )
       {
-#pragma unroll
-	 for( int j = 0; j < 4; j++ )
-	 {
-	    s.cu[j][t] = s.cu[j + 1][t]; s.cv[j][t] = s.cv[j + 1][t]; s.cw[j][t] = s.cw[j + 1][t];
-	    s.amz[j][t] = s.amz[j + 1][t]; s.alz[j][t] = s.alz[j + 1][t];
-	 }
 	 s.cu[R0][t] = q0[0][t]; s.cv[R0][t] = q0[1][t]; s.cw[R0][t] = q0[2][t];
 	 s.amz[R0][t] = m0[t] * szp; s.alz[R0][t] = ( 2 * m0[t] + l0[t] ) * szp;
       }
@@ -630,7 +626,7 @@ __global__ void __launch_bounds__( 16 * TY, 1 ) k_rhs_fast4( const FastArgs a, c
 
    fast4::State s;
 #pragma unroll
-   for( int m = 0; m < 5; m++ )
+   for( int m = 0; m < 6; m++ )
 #pragma unroll
       for( int t = 0; t < 2; t++ ) s.cu[m][t] = s.cv[m][t] = s.cw[m][t] = s.amz[m][t] = s.alz[m][t] = 0;
 #pragma unroll
@@ -678,12 +674,7 @@ __global__ void __launch_bounds__( 16 * TY, 1 ) k_rhs_fast4( const FastArgs a, c
       ph.t0 = 2 * C::NH * m3; ph.t2 = 2 * C::NH * ( ( m3 + 1 ) % 3 );
       fast4::stage<TY, EPI>( a, maps, c, p, ph.slot, ph.par );
    }
-   for( int p = c.ka - 2; p <= plast; p++ )
-   {
-      // the two warps of a scheduler (w, w+4) run the phases of a step in different orders
-      if( STAG && c.tid < NT / 2 ) fast4::step<TY, EPI, 1>( a, maps, c, s, tm, p, ph );
-      else fast4::step<TY, EPI, 0>( a, maps, c, s, tm, p, ph );
-      // next plane
+   auto next_plane = [&]() {
       ph.slot = ph.slot == 5 ? 0 : ph.slot + 1;
 #pragma unroll
       for( int j = 4; j > 0; j-- ) { ph.o[j] = ph.o[j - 1]; ph.c[j] = ph.c[j - 1]; }
@@ -692,6 +683,35 @@ __global__ void __launch_bounds__( 16 * TY, 1 ) k_rhs_fast4( const FastArgs a, c
       ph.par ^= 1;
       ph.t2 = ( ph.t0 == 0 ? 2 : ( ph.t0 == 2 * C::NH ? 0 : 1 ) ) * 2 * C::NH; // slot of plane (p+1)-2 = slot of p+2 mod 3
       ph.t0 = ph.t0 == 4 * C::NH ? 0 : ph.t0 + 2 * C::NH;
+   };
+   auto shift2 = [&]() {
+#pragma unroll
+      for( int t = 0; t < 2; t++ )
+#pragma unroll
+	 for( int j = 0; j < 4; j++ )
+	 {
+	    s.cu[j][t] = s.cu[j + 2][t]; s.cv[j][t] = s.cv[j + 2][t]; s.cw[j][t] = s.cw[j + 2][t];
+	    s.amz[j][t] = s.amz[j + 2][t]; s.alz[j][t] = s.alz[j + 2][t];
+	 }
+   };
+   // (STAG: the two warps of a scheduler (w, w+4) run the phases of a step in different orders)
+   const bool alt = STAG && c.tid < NT / 2;
+   int p = c.ka - 2;
+   if( p & 1 )
+   {
+      if( alt ) fast4::step<TY, EPI, 1, 1>( a, maps, c, s, tm, p, ph );
+      else fast4::step<TY, EPI, 0, 1>( a, maps, c, s, tm, p, ph );
+      shift2(); next_plane(); p++;
+   }
+   while( p <= plast )
+   {
+      if( alt ) fast4::step<TY, EPI, 1, 0>( a, maps, c, s, tm, p, ph );
+      else fast4::step<TY, EPI, 0, 0>( a, maps, c, s, tm, p, ph );
+      next_plane(); p++;
+      if( p > plast ) break;
+      if( alt ) fast4::step<TY, EPI, 1, 1>( a, maps, c, s, tm, p, ph );
+      else fast4::step<TY, EPI, 0, 1>( a, maps, c, s, tm, p, ph );
+      shift2(); next_plane(); p++;
    }
 #if !defined( SW4B200_EMULATE )
    // every warp is done with its strip (its loads were waited for) before the columns go back
