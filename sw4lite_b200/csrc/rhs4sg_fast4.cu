@@ -71,6 +71,20 @@ struct D2 { double x, y; };
 #else
 typedef double2 D2;
 #endif
+// 1/x without the division's slow-path branch: single-precision seed and two Newton steps (error < 1 ulp of the
+// double result for x in the normal range of a float -- x is a density)
+__device__ __forceinline__ double rcp_nr( double x )
+{
+#if defined( __CUDA_ARCH__ )
+   double y = (double)__frcp_rn( (float)x );
+   double e = fma( -x, y, 1.0 );
+   y = fma( y, e, y );
+   e = fma( -x, y, 1.0 );
+   return fma( y, e, y );
+#else
+   return 1.0 / x;
+#endif
+}
 __device__ __forceinline__ D2 ld2( const double* p ) { return *reinterpret_cast<const D2*>( p ); }
 __device__ __forceinline__ void st2( double* p, double x, double y )
 {
@@ -179,7 +193,7 @@ struct Ctx
    int li0, lj0; // local (array) index of the tile's first output
    int tid, txh, ty, o;
    int ka, kb, pend;
-   bool act[2];
+   bool act; // the pair is inside the interior (ni is even and pairs start at even i: never split by the boundary)
    long long gown; // offset of the left point inside a plane
 };
 
@@ -250,7 +264,7 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
    tm.wait_st(); // the records stored by the earlier steps (long done) are readable
 
    const bool kfin = kf >= c.ka && kf <= c.kb;
-   const bool fin[2] = { c.act[0] && kfin, c.act[1] && kfin };
+   const bool fin = c.act && kfin;
    const long long qf = kfin ? b.nij * ( kf - b.kfirst ) + c.gown : 0;
 
    // strx at i-2..i+3 (i = left point), stry at j-2..j+2: re-read every step instead of held in 22 registers
@@ -276,14 +290,14 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
 #pragma unroll
 	 for( int t = 0; t < 2; t++ )
 	 {
-	    const double rh = fin[t] ? pick( e_rho, t ) : 1.0;
+	    const double rh = fin ? pick( e_rho, t ) : 1.0;
 	    if( EPI == EPI_PRED )
 	    {
-	       rinv[t] = 1.0 / rh; // one division per point; dt^2/rho and acc/rho are formed from it
+	       rinv[t] = rcp_nr( rh ); // one reciprocal per point; dt^2/rho and acc/rho are formed from it
 	       fr[t] = a.fac * rinv[t];
 	    }
 	    else
-	       fr[t] = a.fac / rh;
+	       fr[t] = a.fac * rcp_nr( rh );
 	 }
       }
       constexpr int RF = R3; // plane kf = p-3
@@ -318,17 +332,11 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
 	    else
 	       o1[t] = pick( e_um, t ) + fr[t] * r_;
 	 }
-	 // the pair is 16-byte aligned in global memory too (even ni, even li): one store per array unless the right
-	 // point is outside the interior
-	 if( fin[1] )
+	 // the pair is 16-byte aligned in global memory too (even ni, even li): one store per array
+	 if( fin )
 	 {
 	    st2( a.out[m] + qf, o1[0], o1[1] );
 	    if( EPI == EPI_PRED ) st2( a.out2[m] + qf, o2[0], o2[1] );
-	 }
-	 else if( fin[0] )
-	 {
-	    a.out[m][qf] = o1[0];
-	    if( EPI == EPI_PRED ) a.out2[m][qf] = o2[0];
 	 }
       }
    };
@@ -620,8 +628,7 @@ __global__ void __launch_bounds__( 16 * TY, 1 ) k_rhs_fast4( const FastArgs a, c
    for( int t = c.tid; t < 6 * C::NH; t += NT ) smem[C::O_HML + t] = 0.0;
    c.o = ( c.ty + 2 ) * PX + 2 * c.txh + 2; // left own point in a staged plane
    const int li = li0 + 2 * c.txh, lj = lj0 + c.ty;
-   c.act[0] = li <= b.ni - 3 && lj <= b.nj - 3;
-   c.act[1] = li + 1 <= b.ni - 3 && lj <= b.nj - 3;
+   c.act = li + 1 <= b.ni - 3 && lj <= b.nj - 3;
    c.gown = (long long)lj * b.ni + li;
 
    fast4::State s;
