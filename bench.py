@@ -309,11 +309,11 @@ def main_ours(a):
         # DRAM traffic of that kernel from the committed ncu --set full capture (bytes per point, scaled to this launch)
         traffic, traffic_src, kname = None, None, "k_rhs_fast4<16,EPI_PRED> (fused rhs4sg + predictor + acceleration)"
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01d_traffic.json")))
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01e_traffic.json")))
             ent = tr["pred"]
             kname = ent.get("kernel", kname)
             traffic = ent["dram_bytes_per_point"] * a.nx * a.ny * rows / prof["rhs_fast_pred"]["launches_per_step"]
-            traffic_src = "profiles/r01d_traffic.json (ncu dram__bytes_read+write per point of the same kernel, scaled to this launch)"
+            traffic_src = "profiles/r01e_traffic.json (ncu dram__bytes_read+write per point of the same kernel, scaled to this launch)"
         except Exception:
             pass
         roof = {"bound": "hbm", "kernel": kname,
