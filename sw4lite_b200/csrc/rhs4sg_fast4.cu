@@ -29,6 +29,10 @@
 // Also compiled by g++ (SW4B200_EMULATE) for the CPU check of the kernel source (tests/emu).
 #include "common.cuh"
 #include <cstring>
+#ifdef SW4B200_EMULATE
+#include <atomic>
+#include <thread>
+#endif
 #ifndef SW4B200_EMULATE
 #include <cuda.h> // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, libcuda is not linked)
 #endif
@@ -97,9 +101,27 @@ __device__ __forceinline__ void st2( double* p, double x, double y )
 // BX x BY plane box from global to shared memory -- no registers, no LSU queue, no per-thread address arithmetic,
 // out-of-array elements arrive as zeros
 #if defined( SW4B200_EMULATE )
-__device__ __forceinline__ void mbar_init( double*, int ) {}
-__device__ __forceinline__ void mbar_arrive_expect( double*, int ) {}
-__device__ __forceinline__ void mbar_wait( double*, int ) {}
+// (emulation: an mbarrier is 16 bytes = {arrivals per phase, pending arrivals, phase}; one OS thread per CUDA thread)
+struct EmuBar { std::atomic<int> count, pending, phase; };
+__device__ __forceinline__ void mbar_init( double* m, int count )
+{
+   EmuBar* b = reinterpret_cast<EmuBar*>( m );
+   b->count.store( count ); b->pending.store( count ); b->phase.store( 0 );
+}
+__device__ __forceinline__ void mbar_arrive_expect( double* m, int ) // (the emulated tile loads are synchronous and precede it)
+{
+   EmuBar* b = reinterpret_cast<EmuBar*>( m );
+   if( b->pending.fetch_sub( 1 ) == 1 )
+   {
+      b->pending.store( b->count.load() );
+      b->phase.fetch_add( 1 );
+   }
+}
+__device__ __forceinline__ void mbar_wait( double* m, int parity )
+{
+   EmuBar* b = reinterpret_cast<EmuBar*>( m );
+   while( ( b->phase.load() & 1 ) == parity ) std::this_thread::yield();
+}
 template <int BX, int BY>
 __device__ __forceinline__ void tma_tile( double* dst, const TMap* map, const Block& b, int c0, int c1, int c2, double* )
 {
@@ -162,8 +184,8 @@ struct Cfg
    static constexpr int O_SX = O_HML + 6 * NH;		      // [PX]
    static constexpr int O_SY = O_SX + PX;		      // [PY]
    static constexpr int O_SZ = O_SY + PY;		      // [SZMAX]
-   static constexpr int O_MBAR = O_SZ + SZMAX;		      // two mbarriers (even / odd planes)
-   static constexpr int SMEM_DOUBLES = O_MBAR + 2 + 2;	      // + the tensor-memory base address
+   static constexpr int O_MBAR = O_SZ + SZMAX;		      // two mbarriers (even / odd planes), 16 bytes apart
+   static constexpr int SMEM_DOUBLES = O_MBAR + 4 + 2;	      // + the tensor-memory base address
    static_assert( ( PLANE % 16 ) == 0 && ( O_ML % 16 ) == 0 && ( O_OP % 16 ) == 0 && ( ( TX * TY ) % 16 ) == 0, "TMA destinations: 128-byte aligned" );
    static constexpr int REC = 40;			      // tensor-memory columns per plane record
    static constexpr int COLS = 256;			      // columns per warp of a lane quadrant (8 warps)
@@ -219,11 +241,13 @@ __device__ __forceinline__ void stage( const FastArgs& a, const FastMaps& maps, 
    typedef Cfg<TY> C;
    if( p > c.pend + 1 || c.tid != 0 ) return;
    const Block& b = a.b;
-   double* const mbar = F4SM( c ) + C::O_MBAR + par;
+   double* const mbar = F4SM( c ) + C::O_MBAR + 2 * par;
    const int kq = p - 3;
    const bool plane = p <= c.pend; // (the step after the last plane only finishes plane kb)
    const bool ops = EPI != EPI_LU && kq >= c.ka && kq <= c.kb;
+#if !defined( SW4B200_EMULATE )
    mbar_arrive_expect( mbar, ( plane ? 5 * C::PLANE * 8 : 0 ) + ( ops ? 4 * C::TX * TY * 8 : 0 ) );
+#endif
    if( plane )
    {
       const int c0 = c.li0 - 2, c1 = c.lj0 - 2, c2 = p - b.kfirst;
@@ -240,6 +264,9 @@ __device__ __forceinline__ void stage( const FastArgs& a, const FastMaps& maps, 
 #pragma unroll
       for( int m = 0; m < 3; m++ ) tma_tile<C::TX, TY>( d + ( m + 1 ) * C::TX * TY, &maps.um[m], b, c.li0, c.lj0, kq - b.kfirst, mbar );
    }
+#if defined( SW4B200_EMULATE )
+   mbar_arrive_expect( mbar, 0 ); // (after the synchronous copies)
+#endif
 }
 
 __device__ __forceinline__ double pick( const D2& v, int t ) { return t ? v.y : v.x; }
@@ -258,7 +285,7 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
    const Block& b = a.b;
    const int k = p - 2, kf = p - 3;
 
-   mbar_wait( F4SM( c ) + C::O_MBAR + ph.par, ( ph.wpar >> ph.par ) & 1 ); // the rows of plane p have landed
+   mbar_wait( F4SM( c ) + C::O_MBAR + 2 * ph.par, ( ph.wpar >> ph.par ) & 1 ); // the boxes of plane p have landed
    __syncthreads(); // the E products of plane k-1 are visible; slot of plane p-5 is free
    stage<TY, EPI>( a, maps, c, p + 1, ph.slot == NSLOT - 1 ? 0 : ph.slot + 1, ph.par ^ 1 );
    tm.wait_st(); // the records stored by the earlier steps (long done) are readable
@@ -356,8 +383,11 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
       {
 	 // x-direction coefficients mu sx, (2mu+la) sx at i-2..i+3, shared by the two points
 	 double axm[6], axl[6];
+	 const D2 ma = ld2( pm - 2 ), mb = ld2( pm ), mc = ld2( pm + 2 ), la = ld2( pl - 2 ), lb = ld2( pl ), lc = ld2( pl + 2 );
+	 D2 xa[3], xb[3], xc[3];
+#pragma unroll
+	 for( int f = 0; f < 3; f++ ) { xa[f] = ld2( pf[f] - 2 ); xb[f] = ld2( pf[f] ); xc[f] = ld2( pf[f] + 2 ); }
 	 {
-	    const D2 ma = ld2( pm - 2 ), mb = ld2( pm ), mc = ld2( pm + 2 ), la = ld2( pl - 2 ), lb = ld2( pl ), lc = ld2( pl + 2 );
 	    m0[0] = mb.x; m0[1] = mb.y; l0[0] = lb.x; l0[1] = lb.y;
 	    axm[0] = ma.x * csx[0]; axm[1] = ma.y * csx[1]; axm[2] = mb.x * csx[2]; axm[3] = mb.y * csx[3]; axm[4] = mc.x * csx[4]; axm[5] = mc.y * csx[5];
 	    axl[0] = ( 2 * ma.x + la.x ) * csx[0]; axl[1] = ( 2 * ma.y + la.y ) * csx[1]; axl[2] = ( 2 * mb.x + lb.x ) * csx[2];
@@ -373,8 +403,7 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
 #pragma unroll
 	 for( int f = 0; f < 3; f++ )
 	 {
-	    const D2 xa = ld2( pf[f] - 2 ), xb = ld2( pf[f] ), xc = ld2( pf[f] + 2 );
-	    const double x[6] = { xa.x, xa.y, xb.x, xb.y, xc.x, xc.y };
+	    const double x[6] = { xa[f].x, xa[f].y, xb[f].x, xb[f].y, xc[f].x, xc[f].y };
 #pragma unroll
 	    for( int t = 0; t < 2; t++ )
 	    {
@@ -589,14 +618,14 @@ __global__ void __launch_bounds__( 16 * TY, 1 ) k_rhs_fast4( const FastArgs a, c
    if( c.tid == 0 )
    {
       mbar_init( smem + C::O_MBAR, 1 );
-      mbar_init( smem + C::O_MBAR + 1, 1 );
+      mbar_init( smem + C::O_MBAR + 2, 1 );
 #if !defined( SW4B200_EMULATE )
       asm volatile( "fence.mbarrier_init.release.cluster;" ::: "memory" );
 #endif
    }
 #if !defined( SW4B200_EMULATE )
    // all 512 columns of tensor memory: one CTA per SM (shared memory), so nobody else can want them
-   uint32_t* const tm_slot = reinterpret_cast<uint32_t*>( smem + C::O_MBAR + 2 );
+   uint32_t* const tm_slot = reinterpret_cast<uint32_t*>( smem + C::O_MBAR + 4 );
    if( c.tid < 32 )
    {
       asm volatile( "tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"( (uint32_t)__cvta_generic_to_shared( tm_slot ) )
