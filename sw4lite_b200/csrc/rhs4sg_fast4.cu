@@ -830,6 +830,7 @@ int launch_fast4( int epi, const FastArgs& a, cudaStream_t st )
    al |= (uintptr_t)a.out[0] | (uintptr_t)a.out[1] | (uintptr_t)a.out[2];
    if( epi == EPI_PRED && a.out2[0] ) al |= (uintptr_t)a.out2[0] | (uintptr_t)a.out2[1] | (uintptr_t)a.out2[2];
    if( ( a.b.ni & 1 ) || ( al & 15 ) ) return launch_fast2( epi, a, st );
+   if( a.b.ni < fast4::Cfg<16>::PX || a.b.nj < fast4::Cfg<16>::PY ) return launch_fast2( epi, a, st ); // (arrays narrower than one TMA box)
    // dense forcing arrays and a predictor without the stored acceleration are not on the time-stepping path (forcing is
    // injected sparsely, pass A always stores uacc): the operator-level calls that use them take the cp.async kernel too
    if( epi != EPI_LU && a.fo[0] ) return launch_fast2( epi, a, st );
