@@ -61,6 +61,30 @@ def test_rhs4sg_edge_sizes(dev, dims):
     assert relerr(a, b) < TOL
 
 
+@pytest.mark.parametrize("dims", [(32, 16, 14), (34, 18, 20), (62, 30, 15), (64, 32, 16), (96, 47, 21), (130, 33, 12), (30, 16, 12)])
+@pytest.mark.parametrize("onesided", [(0, 0, 0, 0, 0, 0), (0, 0, 0, 0, 1, 1)])
+def test_rhs4sg_tma_path_sizes(dev, dims, onesided):
+    """even ni (= nx + 4 ghost points): the TMA-staged fourth-generation interior kernel (x-pairs, 16-byte accesses,
+    tensor-memory z state); sizes at and around its 32x16 tile and its 36x20 TMA box ((30,16,12): narrower than a
+    box, served by the cp.async kernel)"""
+    box = Box(*dims)
+    f = random_fields(box, seed=11, corder=1)
+    os_ = onesided if box.nk - 4 >= 12 else (0, 0, 0, 0, 0, 0)
+    a = gpu_rhs4sg(dev, 1, box, box.nk - 4, os_, f, 0.7)
+    b = cpu_rhs4sg(1, box, box.nk - 4, os_, f, 0.7)
+    assert relerr(a, b) < TOL
+
+
+def test_rhs4sg_leaves_ghost_points_untouched_even_ni(dev):
+    box = Box(40, 21, 15)
+    f = random_fields(box, seed=4, corder=1)
+    lu0 = np.full(3 * box.npts, 123.0)
+    a = gpu_rhs4sg(dev, 1, box, box.nk - 4, (0,) * 6, f, 1.0, lu0=lu0).reshape(3, box.nk, box.nj, box.ni)
+    inner = np.zeros((box.nk, box.nj, box.ni), dtype=bool)
+    inner[2:-2, 2:-2, 2:-2] = True
+    assert np.all(a[:, ~inner] == 123.0) and np.all(a[:, inner] != 123.0)
+
+
 def test_rhs4sg_leaves_ghost_points_untouched(dev):
     box = Box(20, 17, 15)
     f = random_fields(box, seed=4, corder=1)
