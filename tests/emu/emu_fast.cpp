@@ -44,7 +44,7 @@ extern "C" int emu_rhs_fast( int gen, int epi, int ifirst, int ilast, int jfirst
       a.fo[c] = fo ? fo + c * n : 0;
    }
    a.mu = mu; a.la = la; a.strx = strx; a.stry = stry; a.strz = strz; a.cof6 = cof / 6; a.cof144 = cof / 144; a.rho = rho; a.fac = fac;
-   if( gen == 4 )
+   if( gen == 4 || gen == 41 ) // 4: the product configuration; 41: staggered phase order (A/B variant)
    {
       constexpr int TY4 = 16;
       typedef fast4::Cfg<TY4> C4;
@@ -53,9 +53,18 @@ extern "C" int emu_rhs_fast( int gen, int epi, int ifirst, int ilast, int jfirst
       FastMaps maps; // (the emulated TMA tile load reads through the array base)
       for( int c = 0; c < 3; c++ ) { maps.u[c].base = a.u[c]; maps.um[c].base = a.um[c]; }
       maps.mu.base = a.mu; maps.la.base = a.la; maps.rho.base = a.rho;
-      if( epi == EPI_LU ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_LU, 1>( a, maps ); } );
-      else if( epi == EPI_PRED ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_PRED, 1>( a, maps ); } );
-      else emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_CORR, 1>( a, maps ); } );
+      if( gen == 4 )
+      {
+	 if( epi == EPI_LU ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_LU, 0>( a, maps ); } );
+	 else if( epi == EPI_PRED ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_PRED, 0>( a, maps ); } );
+	 else emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_CORR, 0>( a, maps ); } );
+      }
+      else
+      {
+	 if( epi == EPI_LU ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_LU, 1>( a, maps ); } );
+	 else if( epi == EPI_PRED ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_PRED, 1>( a, maps ); } );
+	 else emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_CORR, 1>( a, maps ); } );
+      }
       return 0;
    }
    if( gen >= 3000 )
