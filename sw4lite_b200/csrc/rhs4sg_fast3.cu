@@ -64,6 +64,7 @@ struct Tm
    __device__ __forceinline__ void st( const double* v, int off = 0 ) { for( int i = 0; i < N; i++ ) mem[( COL + off ) / 2 + i] = v[i]; }
    template <int COL, int N>
    __device__ __forceinline__ void ld( TmVal* r, int off = 0 ) const { for( int i = 0; i < N; i++ ) r[i].v = mem[( COL + off ) / 2 + i]; }
+   __device__ __forceinline__ void st2i( int col, const double* v, int off = 0 ) { mem[( col + off ) / 2] = v[0]; mem[( col + off ) / 2 + 1] = v[1]; }
    __device__ __forceinline__ void wait_st() const {}
    template <int N>
    __device__ __forceinline__ void wait_ld( TmVal* ) const {}
@@ -97,6 +98,14 @@ struct Tm
 		       SW4_HI( v[3] ), SW4_LO( v[4] ), SW4_HI( v[4] ), SW4_LO( v[5] ), SW4_HI( v[5] ), SW4_LO( v[6] ), SW4_HI( v[6] ),
 		       SW4_LO( v[7] ), SW4_HI( v[7] )
 		       : "memory" );
+   }
+   // two doubles to columns col..col+3 (col: a constant after unrolling)
+   __device__ __forceinline__ void st2i( int col, const double* v, int off = 0 )
+   {
+      const uint32_t ta = base + col + off;
+      asm volatile( "tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"( ta ), SW4_LO( v[0] ), SW4_HI( v[0] ), SW4_LO( v[1] ),
+		    SW4_HI( v[1] )
+		    : "memory" );
    }
    template <int COL, int N>
    __device__ __forceinline__ void ld( TmVal* r, int off = 0 ) const

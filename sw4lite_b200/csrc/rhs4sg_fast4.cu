@@ -460,10 +460,11 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
 	 rec[10 + t] = m0[t] * dx[1][t]; // E4 = mu D0x v
 	 rec[12 + t] = e5p;
       }
-      const double rg[8] = { g1n[0], g1n[1], g2n[0], g2n[1], g3n[0], g3n[1], rec[0], rec[1] };
-      tm.template st<0, 8>( rg, ph.c[0] );	    // cols 0-15
-      tm.template st<16, 8>( rec + 2, ph.c[0] ); // cols 16-31
-      tm.template st<32, 4>( rec + 10, ph.c[0] ); // cols 32-39
+      // pair-wise stores (two doubles of a pair are neighbours in registers anyway; 16-register operands had to be packed
+      // with 40 moves per step)
+      tm.template st<0, 2>( g1n, ph.c[0] ); tm.template st<4, 2>( g2n, ph.c[0] ); tm.template st<8, 2>( g3n, ph.c[0] );
+#pragma unroll
+      for( int m = 0; m < 7; m++ ) tm.st2i( 12 + 4 * m, rec + 2 * m, ph.c[0] );
    }
 
    // ---- tensor-memory loads for the z work of plane k (the records were retired by the wait at the top of the
