@@ -48,6 +48,10 @@ int sw4b200_kernel_launch_count( void );   /* number of kernels launched by this
 int sw4b200_profile_enable( int on );
 int sw4b200_profile_reset( void );
 int sw4b200_profile_read( const char* kernel, double* ms_total, long long* launches );
+/* run-time switches between equivalent kernels, for A/B measurements and tests (all default to 1):
+ *   "sgd_zonly"  damping boxes in which only dcz is non-zero take the streaming z-only kernel (bit-identical to the
+ *                general kernel there; the reference has one kernel, addsgd4fort, ew-cfromfort.C:748) */
+int sw4b200_set_option( const char* name, int value );
 
 /* ---------------------------------------------------------------- memory
  * replaces Sarray::allocate_on_device / copy_to_device / copy_from_device / page_lock

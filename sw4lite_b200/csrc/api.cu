@@ -933,6 +933,7 @@ static void build_sgd_boxes( sw4b200_grid* g )
    g->sgd_boxes_valid = true;
 }
 
+static int g_opt_sgd_zonly = 1; // sw4b200_set_option( "sgd_zonly", . )
 static int damping_dev( sw4b200_grid* g, int part )
 {
    if( g->d.sg_order == 0 || g->d.beta == 0 ) return 0;
@@ -947,7 +948,7 @@ static int damping_dev( sw4b200_grid* g, int part )
 	 if( box.v[4] < ka ) box.v[4] = ka;
 	 if( box.v[5] > kb ) box.v[5] = kb;
 	 if( box.v[5] < box.v[4] ) continue;
-	 if( ( *g->sgd_zonly )[ib] && g->d.corder == 1 )
+	 if( ( *g->sgd_zonly )[ib] && g->d.corder == 1 && g_opt_sgd_zonly )
 	 {
 	    if( launch_addsgd4_zonly( g->b, box, g->Up, g->U, g->Um, g->rho, g->dc[2], g->str[2], g->co[0], g->co[1], g->d.beta, g->st ) )
 	       return 1;
@@ -1195,6 +1196,12 @@ int sw4b200_grid_set_stream( sw4b200_grid* g, int st )
    if( st < 0 || st >= 4 ) return set_error( "grid_set_stream: bad stream %d", st );
    g->st = g_streams[st];
    return 0;
+}
+
+int sw4b200_set_option( const char* name, int value )
+{
+   if( name && !strcmp( name, "sgd_zonly" ) ) { g_opt_sgd_zonly = value != 0; return 0; }
+   return set_error( "set_option: unknown option '%s'", name ? name : "(null)" );
 }
 
 int sw4b200_profile_enable( int on )

@@ -35,6 +35,7 @@ SIGNATURES = {
     "sw4b200_sync_device": (I, []),
     "sw4b200_kernel_launch_count": (I, []),
     "sw4b200_profile_enable": (I, [I]),
+    "sw4b200_set_option": (I, [C.c_char_p, I]),
     "sw4b200_profile_reset": (I, []),
     "sw4b200_profile_read": (I, [C.c_char_p, c_dp, c_llp]),
     "sw4b200_malloc": (VP, [C.c_size_t]),

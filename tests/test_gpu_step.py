@@ -109,6 +109,30 @@ def test_synthetic_block_steps_match_oracle(corder):
         assert relerr(blk.download("U"), cpu.U) < 1e-12, "step %d" % (step + 1)
 
 
+def test_damping_zonly_kernel_is_bit_identical_to_the_general_kernel():
+    """boxes in which only dcz is non-zero take the streaming z-only damping kernel: same bits as the general kernel"""
+    import sw4lite_b200 as S
+    from sw4lite_b200.setup import CartesianProblem
+    prob = CartesianProblem(70, 66, 40, h=100.0, gp=8, corder=1, layers=[(1500.0, 6000.0, 3464.0, 2700.0)])
+    prob.add_point_force(30, 28, 9, (1e12, 2e12, -1e12), freq=2.0, t0=0.0)
+    u0, um0 = _initial(prob)
+    out = []
+    lib = S.load()
+    try:
+        for zonly in (1, 0):
+            S.lib.check(lib.sw4b200_set_option(b"sgd_zonly", zonly))
+            blk = prob.make_block()
+            blk.upload("U", u0); blk.upload("Um", um0)
+            n0 = lib.sw4b200_kernel_launch_count()
+            for s in range(3):
+                blk.step(prob.forces(s * prob.dt), prob.forces(s * prob.dt, tt=True))
+            out.append((blk.download("U"), lib.sw4b200_kernel_launch_count() - n0))
+    finally:
+        S.lib.check(lib.sw4b200_set_option(b"sgd_zonly", 1))
+    assert np.array_equal(out[0][0], out[1][0])
+    assert out[0][1] == out[1][1] > 0   # same boxes either way, only the kernel of the z-only boxes differs
+
+
 def test_resident_run_equals_stepwise_and_records():
     """sw4b200_grid_run (sources/receivers device resident, no host sync) == the per-step API, bit for bit"""
     prob = _problem()
