@@ -168,6 +168,9 @@ __global__ void __launch_bounds__( 256 ) k_addsgd4_zonly( Block b, Int6 box, int
       }
    }
    rh[0] = 0; rh[1] = rho[b.nij * ( ka - 1 ) + own]; rh[2] = rho[b.nij * ka + own];
+   double upn[3]; // up of the next plane, fetched one plane ahead
+#pragma unroll
+   for( int c = 0; c < 3; c++ ) upn[c] = up[c * b.npts + b.nij * ka + own];
    for( int k = ka; k <= kb; k++ )
    {
 #pragma unroll
@@ -176,9 +179,15 @@ __global__ void __launch_bounds__( 256 ) k_addsgd4_zonly( Block b, Int6 box, int
 	 for( int m = 0; m < 4; m++ ) d[c][m] = d[c][m + 1];
       rh[0] = rh[1]; rh[1] = rh[2];
       const long long q = b.nij * k + own, q2 = q + 2 * b.nij;
+      const double upv[3] = { upn[0], upn[1], upn[2] };
 #pragma unroll
       for( int c = 0; c < 3; c++ ) d[c][4] = u[c * b.npts + q2] - um[c * b.npts + q2];
       rh[2] = rho[q + b.nij];
+      if( k < kb )
+      {
+#pragma unroll
+	 for( int c = 0; c < 3; c++ ) upn[c] = up[c * b.npts + q + b.nij];
+      }
       const double prez = strz[k] * cxi * cyj; // as k_addsgd4_fast forms it
       const double birho = beta / rh[1];
       const double czm = dcz[k - 1], cz0 = dcz[k], czp = dcz[k + 1];
@@ -186,7 +195,7 @@ __global__ void __launch_bounds__( 256 ) k_addsgd4_zonly( Block b, Int6 box, int
       for( int c = 0; c < 3; c++ )
       {
 	 const double s = prez * sg_term( d[c][0], d[c][1], d[c][2], d[c][3], d[c][4], rh[0], rh[1], rh[2], czm, cz0, czp );
-	 up[c * b.npts + q] = up[c * b.npts + q] - birho * s;
+	 up[c * b.npts + q] = upv[c] - birho * s;
       }
    }
 }
