@@ -19,6 +19,13 @@
 //     the five-plane rings of u,v,w, mu sz, (2mu+la) sz of the two points;
 //   * mu and la are needed in shared memory only for the plane that arrives (2 slots instead of 6; the ring points
 //     of the tile keep a 3-deep side copy), which is what lets a 32x16 tile fit in 227 KB.
+//   * planes arrive by TMA tile loads (cp.async.bulk.tensor.3d on 3-D tensor maps of the arrays: one request per
+//     field and plane, issued by one thread, completing on an mbarrier per plane parity, out-of-array elements
+//     zero-filled): no LDGSTS, no per-thread address arithmetic;
+//   * the march has two step bodies (even / odd planes) over six-deep register arrays shifted by two: half the
+//     register moves of a shift register, and a third of the code of the six-fold unrolled ring (which overflowed
+//     the instruction cache).
+// Measured history and what was tried on top: profiles/r01d_k_rhs_fast4_ncu.md.
 // sz is folded into the z-type exchanged products (E3 = mu sz D0z u, E6 = mu sz D0z v) and la sz = (2mu+la)sz - 2 mu sz
 // comes from the register rings, so mu, la themselves need no delay line.
 //
