@@ -7,6 +7,7 @@
 // Reference semantics: rhs4sg.C:38-849 / rhs4sg_rev.C:44-864 (L(u)), ew-cfromfort.C:40-141
 // (corrector, predictor, dpdmt), :748-1160 (supergrid damping), :205-745 (bcfortsg).
 #include "common.cuh"
+#include "tma.cuh"
 #include "sbp4_constexpr.h"
 #include <cstdlib>
 
@@ -404,7 +405,7 @@ __global__ void __launch_bounds__( CL_TX* CL_TY ) k_closure_staged( RhsArgs a, i
 // 32x8 tile, rows kb_lo..kb_hi of one side.  Agrees with rhs_closure_point to rounding (different association).
 constexpr int CF_EX = 3 * CL_TY * CL_PX, CF_EY = 3 * CL_PY * CL_TX;
 constexpr int CF_OPS = 6 * 4 * CL_TX * CL_TY; // epilogue operands (rho, um or up) of the own points of the 6 rows
-constexpr int CF_SMEM_DOUBLES = 5 * CL_NP * CL_PLANE + CF_EX + CF_EY + CL_PX + CL_PY + CF_OPS;
+constexpr int CF_SMEM_DOUBLES = 5 * CL_NP * CL_PLANE + CF_EX + CF_EY + CL_PX + CL_PY + CF_OPS + 2; // + one mbarrier (TMA staging)
 
 __device__ __forceinline__ void cf_cp_async8( double* sdst, const double* gsrc, bool valid )
 {
@@ -418,23 +419,52 @@ __device__ __forceinline__ double cf_d0u( double fm2, double fm1, double fp1, do
    return ( fm2 - fp2 ) + 8 * ( fp1 - fm1 ); // 12 * centred first difference
 }
 
-template <int MODE>
-__global__ void __launch_bounds__( CL_TX* CL_TY, 1 ) k_closure_fast( RhsArgs a, int side, int kb_lo, int kb_hi )
+// TMA: the 9 halo'd planes of u,v,w,mu,la arrive as ONE 36x12x9 box per field and the epilogue operands as one 32x8x6
+// box per array (tma.cuh; even ni, 16-byte aligned arrays), instead of 45 + 24 cp.async per thread with their 64-bit
+// address arithmetic -- that staging phase was 46 % of the kernel's time (profiles/r01h_closure_ncu.md).
+template <int MODE, bool TMA>
+__global__ void __launch_bounds__( CL_TX* CL_TY, 1 ) k_closure_fast( RhsArgs a, int side, int kb_lo, int kb_hi, const __grid_constant__ FastMaps maps )
 {
-   extern __shared__ double sm[];
+   extern __shared__ __align__( 128 ) double sm_cl[];
+   double* const sm = sm_cl;
    constexpr int TX = CL_TX, TY = CL_TY, PX = CL_PX, PY = CL_PY, PLANE = CL_PLANE, NP = CL_NP, NT = CL_TX * CL_TY;
    double* const s_f = sm;				 // [5 fields][9 planes][PLANE]
    double* const s_ex = sm + 5 * NP * PLANE;		 // [3][TY][PX]
    double* const s_ey = s_ex + CF_EX;			 // [3][PY][TX]
    double* const s_sx = s_ey + CF_EY;			 // [PX]
    double* const s_sy = s_sx + PX;			 // [PY]
-   double* const s_op = s_sy + PY;			 // [6 rows][4][NT]
+   double* const s_op = s_sy + PY;			 // [6 rows][4][NT]   (TMA: [4][6 planes][NT])
+   double* const s_mbar = s_op + CF_OPS;
+   // operand f (0: rho, 1..3: um / up) of closure row kb at the thread's own point
+   auto opidx = [&]( int kb, int f ) { return TMA ? ( f * 6 + ( side == 0 ? kb - 1 : 6 - kb ) ) * NT : ( ( kb - 1 ) * 4 + f ) * NT; };
    constexpr bool STAGED_OPS = MODE == MODE_PRED || MODE == MODE_CORR_ACC;
    const Block& b = a.b;
    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
    const int li0 = 2 + blockIdx.x * TX, lj0 = 2 + blockIdx.y * TY;
    const int kbase = side == 0 ? 0 : a.nk - 7; // global k of staged plane 0
-   if( STAGED_OPS && li0 + tx <= b.ni - 3 && lj0 + ty <= b.nj - 3 )
+   if( TMA )
+   {
+      using namespace fast4;
+      if( tid == 0 )
+      {
+	 mbar_init( s_mbar, 1 );
+	 asm volatile( "fence.mbarrier_init.release.cluster;" ::: "memory" );
+	 mbar_arrive_expect( s_mbar, 5 * NP * PLANE * 8 + ( STAGED_OPS ? CF_OPS * 8 : 0 ) );
+	 const int c0 = li0 - 2, c1 = lj0 - 2, c2 = kbase - b.kfirst;
+#pragma unroll
+	 for( int f = 0; f < 3; f++ ) tma_tile<PX, PY, NP>( s_f + f * NP * PLANE, &maps.u[f], b, c0, c1, c2, s_mbar );
+	 tma_tile<PX, PY, NP>( s_f + 3 * NP * PLANE, &maps.mu, b, c0, c1, c2, s_mbar );
+	 tma_tile<PX, PY, NP>( s_f + 4 * NP * PLANE, &maps.la, b, c0, c1, c2, s_mbar );
+	 if( STAGED_OPS )
+	 {
+	    const int k0 = ( side == 0 ? 1 : a.nk - 5 ) - b.kfirst; // rows 1..6 / nk-5..nk, in increasing k
+	    tma_tile<TX, TY, 6>( s_op, &maps.rho, b, li0, lj0, k0, s_mbar );
+#pragma unroll
+	    for( int c = 0; c < 3; c++ ) tma_tile<TX, TY, 6>( s_op + ( c + 1 ) * 6 * NT, &maps.um[c], b, li0, lj0, k0, s_mbar );
+	 }
+      }
+   }
+   if( !TMA && STAGED_OPS && li0 + tx <= b.ni - 3 && lj0 + ty <= b.nj - 3 )
    {
       // epilogue operands of the thread's own points: in flight together with the planes
       for( int kb = kb_lo; kb <= kb_hi; kb++ )
@@ -449,7 +479,7 @@ __global__ void __launch_bounds__( CL_TX* CL_TY, 1 ) k_closure_fast( RhsArgs a, 
       }
    }
    const double dt2i = 1.0 / ( a.dt * a.dt );
-   for( int idx = tid; idx < PLANE; idx += NT )
+   for( int idx = tid; !TMA && idx < PLANE; idx += NT )
    {
       const int sy_ = idx / PX, sx_ = idx - sy_ * PX;
       const int li = li0 - 2 + sx_, lj = lj0 - 2 + sy_;
@@ -479,13 +509,14 @@ __global__ void __launch_bounds__( CL_TX* CL_TY, 1 ) k_closure_fast( RhsArgs a, 
 	 }
       }
    }
-   if( MODE != MODE_CORR ) asm volatile( "cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory" );
+   if( !TMA && MODE != MODE_CORR ) asm volatile( "cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory" );
    for( int t = tid; t < PX + PY; t += NT )
    {
       if( t < PX ) { const int li = li0 - 2 + t; s_sx[t] = li < b.ni ? a.strx[li] : 0.0; }
       else { const int lj = lj0 - 2 + ( t - PX ); s_sy[t - PX] = lj < b.nj ? a.stry[lj] : 0.0; }
    }
    __syncthreads();
+   if( TMA ) fast4::mbar_wait( s_mbar, 0 ); // the boxes have landed (the barrier above published the initialised mbarrier)
    // closure row q (1..8; 0 = ghost plane) lives in staged plane q (low side) or 8-q (high side)
    const int pbase = side == 0 ? 0 : 8 * PLANE, pstr = side == 0 ? PLANE : -PLANE;
    const double sgn = side == 0 ? 1.0 : -1.0;
@@ -650,8 +681,8 @@ __global__ void __launch_bounds__( CL_TX* CL_TY, 1 ) k_closure_fast( RhsArgs a, 
 	 if( STAGED_OPS )
 	 {
 	    // rhs_epilogue<MODE> with rho, um / up taken from the staged operands and u from the staged plane
-	    const double* const d = s_op + ( kb - 1 ) * 4 * NT + tid;
-	    const double rho = d[0];
+	    const double* const d = s_op + tid;
+	    const double rho = d[opidx( kb, 0 )];
 	    const double uk[3] = { u0, v0, w0 };
 	    const double dt2 = a.dt * a.dt;
 	    const double f = MODE == MODE_PRED ? dt2 / rho : ( dt2 * dt2 / 12 ) / rho;
@@ -663,11 +694,11 @@ __global__ void __launch_bounds__( CL_TX* CL_TY, 1 ) k_closure_fast( RhsArgs a, 
 	       const double acc = cof * r[c] + fo;
 	       if( MODE == MODE_PRED )
 	       {
-		  a.out[q] = 2 * uk[c] - d[( c + 1 ) * NT] + f * acc;
+		  a.out[q] = 2 * uk[c] - d[opidx( kb, c + 1 )] + f * acc;
 		  if( a.out2 ) a.out2[q] = acc / rho;
 	       }
 	       else
-		  a.out[q] = d[( c + 1 ) * NT] + f * acc;
+		  a.out[q] = d[opidx( kb, c + 1 )] + f * acc;
 	    }
 	 }
 	 else
@@ -993,14 +1024,14 @@ static int closure_generation()
    return v;
 }
 
-template <int MODE>
-static int launch_closure_fast_t( const RhsArgs& a, int side, int kb_lo, int kb_hi, cudaStream_t st )
+template <int MODE, bool TMA>
+static int launch_closure_fast_tt( const RhsArgs& a, int side, int kb_lo, int kb_hi, const FastMaps& maps, cudaStream_t st )
 {
    static bool configured = false;
    const size_t smem = (size_t)CF_SMEM_DOUBLES * sizeof( double );
    if( !configured )
    {
-      cudaError_t e = cudaFuncSetAttribute( k_closure_fast<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem );
+      cudaError_t e = cudaFuncSetAttribute( k_closure_fast<MODE, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem );
       if( e != cudaSuccess ) return set_error( "k_closure_fast: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString( e ) );
       configured = true;
    }
@@ -1008,9 +1039,36 @@ static int launch_closure_fast_t( const RhsArgs& a, int side, int kb_lo, int kb_
    ProfScope prof( "closure", st );
    dim3 bs( CL_TX, CL_TY, 1 );
    dim3 gs( ( b.ni - 4 + CL_TX - 1 ) / CL_TX, ( b.nj - 4 + CL_TY - 1 ) / CL_TY, 1 );
-   k_closure_fast<MODE><<<gs, bs, smem, st>>>( a, side, kb_lo, kb_hi );
+   k_closure_fast<MODE, TMA><<<gs, bs, smem, st>>>( a, side, kb_lo, kb_hi, maps );
    count_launch();
    return check_launch( "k_closure_fast" );
+}
+
+template <int MODE>
+static int launch_closure_fast_t( const RhsArgs& a, int side, int kb_lo, int kb_hi, cudaStream_t st )
+{
+   const Block& b = a.b;
+   FastMaps maps;
+   memset( &maps, 0, sizeof( maps ) );
+   // TMA staging needs tensor maps: SoA layout, even ni (row pitch a multiple of 16 bytes), 16-byte aligned arrays, arrays at
+   // least one box wide; MODE_CORR forms its input on the fly and keeps the direct loads
+   constexpr bool staged_ops = MODE == MODE_PRED || MODE == MODE_CORR_ACC;
+   const double* const ops = MODE == MODE_PRED ? a.um : a.up;
+   uintptr_t al = (uintptr_t)a.u | (uintptr_t)a.mu | (uintptr_t)a.la;
+   if( staged_ops ) al |= (uintptr_t)a.rho | (uintptr_t)ops;
+   const bool tma = MODE != MODE_CORR && b.sp == 1 && !( b.ni & 1 ) && !( b.npts & 1 ) && !( al & 15 ) && b.ni >= CL_PX && b.nj >= CL_PY &&
+		    b.nk >= CL_NP;
+   if( !tma ) return launch_closure_fast_tt<MODE, false>( a, side, kb_lo, kb_hi, maps, st );
+   for( int c = 0; c < 3; c++ )
+      if( make_tmap( &maps.u[c], a.u + c * b.sc, b, CL_PX, CL_PY, CL_NP ) ) return 1;
+   if( make_tmap( &maps.mu, a.mu, b, CL_PX, CL_PY, CL_NP ) || make_tmap( &maps.la, a.la, b, CL_PX, CL_PY, CL_NP ) ) return 1;
+   if( staged_ops )
+   {
+      if( make_tmap( &maps.rho, a.rho, b, CL_TX, CL_TY, 6 ) ) return 1;
+      for( int c = 0; c < 3; c++ )
+	 if( make_tmap( &maps.um[c], ops + c * b.sc, b, CL_TX, CL_TY, 6 ) ) return 1;
+   }
+   return launch_closure_fast_tt<MODE, true>( a, side, kb_lo, kb_hi, maps, st );
 }
 
 template <int MODE>
