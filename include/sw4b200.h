@@ -214,13 +214,17 @@ typedef struct
 
 sw4b200_grid* sw4b200_grid_create( const sw4b200_grid_desc* desc );
 int sw4b200_grid_destroy( sw4b200_grid* g );
-/* names: "U","Um","Up" (3*npts), "mu","lambda","rho","jac" (npts), "metric" (4*npts),
+/* names: "U","Um","Up","Uacc" (3*npts), "mu","lambda","rho","jac" (npts), "metric" (4*npts),
  * "strx","dcx","cox" (ni), "stry","dcy","coy" (nj), "strz","dcz","coz" (nk),
- * "bforce0".."bforce5" (3*points of the side window). */
+ * "bforce0".."bforce5" (3*points of the side window).  Host arrays are always in the reference's
+ * Sarray layout (Sarray.C:753-778) with npts = ni*nj*nk.  On the device the rows of an (i,j,k,c) block with odd
+ * ni are padded to an even pitch (sw4b200_grid_row_pitch doubles; 16-byte aligned rows for the TMA-staged
+ * kernels): upload/download convert, code that uses sw4b200_grid_device_ptr must honour the pitch. */
 int sw4b200_grid_upload( sw4b200_grid* g, const char* name, const double* h_src );
 int sw4b200_grid_download( sw4b200_grid* g, const char* name, double* h_dst );
 void* sw4b200_grid_device_ptr( sw4b200_grid* g, const char* name );
-size_t sw4b200_grid_array_size( sw4b200_grid* g, const char* name ); /* number of doubles */
+size_t sw4b200_grid_array_size( sw4b200_grid* g, const char* name ); /* number of doubles (host view) */
+int sw4b200_grid_row_pitch( sw4b200_grid* g );                       /* device row pitch in doubles (ni or ni+1) */
 /* unique source points of this block: (i,j,k) global indices, n points */
 int sw4b200_grid_set_source_points( sw4b200_grid* g, int n, const int* h_ijk /*3*n*/ );
 /* receivers (displacement) */

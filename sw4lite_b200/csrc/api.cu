@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 #include <map>
+#include <algorithm>
 
 namespace sw4b200 {
 
@@ -141,23 +142,31 @@ static void fast_args( const RhsArgs& a, FastArgs& f )
    }
 }
 
-// scratch array for the API-level corrector (uacc of the whole block)
-static double* g_scratch = 0;
-static size_t g_scratch_cap = 0;
-static double* scratch( size_t doubles )
+// scratch array for the API-level corrector (uacc of the whole block), one per stream: calls on different streams
+// must not share it
+struct Scratch { double* p; size_t cap; };
+static std::map<cudaStream_t, Scratch> g_scratch;
+static double* scratch( cudaStream_t st, size_t doubles )
 {
-   if( doubles > g_scratch_cap )
+   Scratch& sc = g_scratch[st];
+   if( doubles > sc.cap )
    {
-      if( g_scratch ) cudaFree( g_scratch );
-      g_scratch = 0; g_scratch_cap = 0;
-      if( cudaMalloc( (void**)&g_scratch, doubles * sizeof( double ) ) != cudaSuccess )
+      if( sc.p ) cudaFree( sc.p );
+      sc.p = 0; sc.cap = 0;
+      if( cudaMalloc( (void**)&sc.p, doubles * sizeof( double ) ) != cudaSuccess )
       {
 	 set_error( "cannot allocate %zu bytes of scratch", doubles * sizeof( double ) );
 	 return 0;
       }
-      g_scratch_cap = doubles;
+      sc.cap = doubles;
    }
-   return g_scratch;
+   return sc.p;
+}
+static void free_scratch()
+{
+   for( auto& kv : g_scratch )
+      if( kv.second.p ) cudaFree( kv.second.p );
+   g_scratch.clear();
 }
 
 // L(u) rows [r0,r1] by the fast kernel where possible and the general kernel on closure rows.
@@ -201,12 +210,12 @@ static int run_rhs( RhsMode mode, const RhsArgs& a_in, int corder, cudaStream_t 
    RhsArgs a = a_in;
    const int r0 = a.b.kfirst + 2, r1 = a.b.klast - 2;
    int rc;
-   if( corder && use_fast_path() && a.b.ni >= 5 && a.b.nj >= 5 )
+   if( corder && use_fast_path() && a.b.nil >= 5 && a.b.nj >= 5 )
    {
       if( mode == MODE_CORR )
       {
 	 // uacc of the whole block, then corrector (out of place) and supergrid damping
-	 double* ua = scratch( 3 * (size_t)a.b.npts );
+	 double* ua = scratch( st, 3 * (size_t)a.b.npts );
 	 if( !ua ) return 1;
 	 if( launch_dpdmt( 3 * a.b.npts, a.up, a.u, a.um, ua, 1.0 / ( a.dt * a.dt ), st ) ) return 1;
 	 RhsArgs c = a;
@@ -258,7 +267,6 @@ struct sw4b200_grid
    int nrec;
    long long* d_recidx;
    double *d_rec, *h_rec;
-   double* halo_buf[2];
 };
 
 extern "C" {
@@ -271,8 +279,12 @@ int sw4b200_init( int device )
       return set_error( "sw4b200_init: no CUDA device (%s); this library has no CPU fallback",
 			e != cudaSuccess ? cudaGetErrorString( e ) : "device count 0" );
    if( device < 0 || device >= n ) return set_error( "sw4b200_init: device %d out of range [0,%d)", device, n );
+   // one device per process (the reference runs one MPI rank per GPU the same way, EW_cuda.C:560-650): streams, the
+   // constant-memory tables and the kernels' shared-memory attributes are set up for that device only
+   if( g_init && g_device != device )
+      return set_error( "sw4b200_init: this process already drives device %d; one device per process (call sw4b200_finalize first)", g_device );
    CUDA_OK( cudaSetDevice( device ) );
-   if( g_init && g_device == device ) return 0;
+   if( g_init ) return 0;
    cudaDeviceProp prop;
    CUDA_OK( cudaGetDeviceProperties( &prop, device ) );
    if( prop.major < 10 )
@@ -292,7 +304,9 @@ int sw4b200_finalize( void )
    cudaDeviceSynchronize();
    for( int s = 0; s < 4; s++ )
       if( g_streams[s] ) { cudaStreamDestroy( g_streams[s] ); g_streams[s] = 0; }
+   free_scratch();
    g_init = false;
+   g_device = -1;
    return 0;
 }
 
@@ -595,20 +609,24 @@ int sw4b200_rhs4sg_host( int corder, int ifirst, int ilast, int jfirst, int jlas
 }
 
 // ------------------------------------------------------------------ grid-block solver object
-static double** grid_array( sw4b200_grid* g, const char* name, size_t* n )
+// array `name` of the block: *n = number of values the caller sees (rows without padding), *nc = components of a
+// field array (its device rows have the pitch b.ni), 0 for 1-D and boundary-forcing arrays
+static double** grid_array( sw4b200_grid* g, const char* name, size_t* n, int* nc )
 {
    const std::string w( name );
-   const size_t np = (size_t)g->b.npts;
-   if( w == "U" ) { *n = 3 * np; return &g->U; }
-   if( w == "Um" ) { *n = 3 * np; return &g->Um; }
-   if( w == "Up" ) { *n = 3 * np; return &g->Up; }
-   if( w == "mu" ) { *n = np; return &g->mu; }
-   if( w == "lambda" ) { *n = np; return &g->la; }
-   if( w == "rho" ) { *n = np; return &g->rho; }
-   if( w == "jac" ) { *n = np; return &g->jac; }
-   if( w == "metric" ) { *n = 4 * np; return &g->met; }
+   const size_t np = (size_t)g->b.nil * g->b.nj * g->b.nk;
+   *nc = 0;
+   if( w == "U" ) { *nc = 3; *n = 3 * np; return &g->U; }
+   if( w == "Um" ) { *nc = 3; *n = 3 * np; return &g->Um; }
+   if( w == "Up" ) { *nc = 3; *n = 3 * np; return &g->Up; }
+   if( w == "Uacc" ) { *nc = 3; *n = 3 * np; return &g->Uacc; }
+   if( w == "mu" ) { *nc = 1; *n = np; return &g->mu; }
+   if( w == "lambda" ) { *nc = 1; *n = np; return &g->la; }
+   if( w == "rho" ) { *nc = 1; *n = np; return &g->rho; }
+   if( w == "jac" ) { *nc = 1; *n = np; return &g->jac; }
+   if( w == "metric" ) { *nc = 4; *n = 4 * np; return &g->met; }
    const char* dn[3] = { "x", "y", "z" };
-   const size_t dl[3] = { (size_t)g->b.ni, (size_t)g->b.nj, (size_t)g->b.nk };
+   const size_t dl[3] = { (size_t)g->b.nil, (size_t)g->b.nj, (size_t)g->b.nk };
    for( int d = 0; d < 3; d++ )
    {
       if( w == std::string( "str" ) + dn[d] ) { *n = dl[d]; return &g->str[d]; }
@@ -624,17 +642,29 @@ static double** grid_array( sw4b200_grid* g, const char* name, size_t* n )
    return 0;
 }
 
-sw4b200_grid* sw4b200_grid_create( const sw4b200_grid_desc* desc )
+// host <-> device copy of an array of the block; field arrays of a padded block move row by row
+static int grid_copy( sw4b200_grid* g, double* dev, double* host, size_t n, int nc, bool to_device )
 {
-   if( need_init() ) return 0;
-   if( check_bounds( desc->ifirst, desc->ilast, desc->jfirst, desc->jlast, desc->kfirst, desc->klast ) ) return 0;
-   sw4b200_grid* g = new sw4b200_grid;
-   memset( g, 0, sizeof( *g ) );
-   g->d = *desc;
-   g->b = make_block( desc->corder, desc->ifirst, desc->ilast, desc->jfirst, desc->jlast, desc->kfirst, desc->klast );
-   g->st = g_streams[0];
+   const Block& b = g->b;
+   if( nc == 0 || b.ni == b.nil )
+   {
+      if( to_device ) CUDA_OK( cudaMemcpyAsync( dev, host, n * 8, cudaMemcpyHostToDevice, g->st ) );
+      else CUDA_OK( cudaMemcpyAsync( host, dev, n * 8, cudaMemcpyDeviceToHost, g->st ) );
+   }
+   else
+   {
+      const size_t rows = (size_t)nc * b.nj * b.nk, w = (size_t)b.nil * 8, dp = (size_t)b.ni * 8;
+      if( to_device ) CUDA_OK( cudaMemcpy2DAsync( dev, dp, host, w, w, rows, cudaMemcpyHostToDevice, g->st ) );
+      else CUDA_OK( cudaMemcpy2DAsync( host, w, dev, dp, w, rows, cudaMemcpyDeviceToHost, g->st ) );
+   }
+   CUDA_OK( cudaStreamSynchronize( g->st ) );
+   return 0;
+}
+
+static int grid_alloc( sw4b200_grid* g )
+{
+   const sw4b200_grid_desc* desc = &g->d;
    const size_t np = (size_t)g->b.npts;
-   g->fast = desc->corder == 1 && !desc->curvilinear && use_fast_path();
    for( int d = 0; d < 3; d++ ) g->h_dc[d] = new std::vector<double>();
    g->sgd_boxes = new std::vector<Int6>();
    g->sgd_zonly = new std::vector<int>();
@@ -642,18 +672,33 @@ sw4b200_grid* sw4b200_grid_create( const sw4b200_grid_desc* desc )
    for( int a = 0; a < 4; a++ )
    {
       *three[a] = (double*)sw4b200_malloc( 3 * np * 8 );
-      if( !*three[a] ) return 0;
+      if( !*three[a] ) return 1;
       cudaMemsetAsync( *three[a], 0, 3 * np * 8, g->st );
    }
    double** one[3] = { &g->mu, &g->la, &g->rho };
    for( int a = 0; a < 3; a++ )
-      if( !( *one[a] = (double*)sw4b200_malloc( np * 8 ) ) ) return 0;
+   {
+      if( !( *one[a] = (double*)sw4b200_malloc( np * 8 ) ) ) return 1;
+      cudaMemsetAsync( *one[a], 0, np * 8, g->st );
+   }
    if( desc->curvilinear )
    {
-      if( !( g->jac = (double*)sw4b200_malloc( np * 8 ) ) ) return 0;
-      if( !( g->met = (double*)sw4b200_malloc( 4 * np * 8 ) ) ) return 0;
-      if( !( g->Lu = (double*)sw4b200_malloc( 3 * np * 8 ) ) ) return 0;
+      if( !( g->jac = (double*)sw4b200_malloc( np * 8 ) ) ) return 1;
+      if( !( g->met = (double*)sw4b200_malloc( 4 * np * 8 ) ) ) return 1;
+      if( !( g->Lu = (double*)sw4b200_malloc( 3 * np * 8 ) ) ) return 1;
+      cudaMemsetAsync( g->jac, 0, np * 8, g->st );
+      cudaMemsetAsync( g->met, 0, 4 * np * 8, g->st );
       cudaMemsetAsync( g->Lu, 0, 3 * np * 8, g->st );
+   }
+   if( g->b.ni != g->b.nil )
+   {
+      // pad column of the divisors: 1, so that the elementwise kernels that sweep the whole allocation stay finite there
+      std::vector<double> ones( (size_t)g->b.nj * g->b.nk, 1.0 );
+      double* divs[2] = { g->rho, g->jac };
+      for( double* dvp : divs )
+	 if( dvp && cudaMemcpy2DAsync( dvp + g->b.nil, (size_t)g->b.ni * 8, ones.data(), 8, 8, ones.size(), cudaMemcpyHostToDevice, g->st ) != cudaSuccess )
+	    return set_error( "grid_create: initialising the pad column failed" );
+      cudaStreamSynchronize( g->st );
    }
    const size_t dl[3] = { (size_t)g->b.ni, (size_t)g->b.nj, (size_t)g->b.nk };
    for( int d = 0; d < 3; d++ )
@@ -661,7 +706,7 @@ sw4b200_grid* sw4b200_grid_create( const sw4b200_grid_desc* desc )
       g->str[d] = (double*)sw4b200_malloc( dl[d] * 8 );
       g->dc[d] = (double*)sw4b200_malloc( dl[d] * 8 );
       g->co[d] = (double*)sw4b200_malloc( dl[d] * 8 );
-      if( !g->str[d] || !g->dc[d] || !g->co[d] ) return 0;
+      if( !g->str[d] || !g->dc[d] || !g->co[d] ) return 1;
       std::vector<double> ones( dl[d], 1.0 ), zeros( dl[d], 0.0 );
       cudaMemcpy( g->str[d], ones.data(), dl[d] * 8, cudaMemcpyHostToDevice );
       cudaMemcpy( g->co[d], ones.data(), dl[d] * 8, cudaMemcpyHostToDevice );
@@ -678,14 +723,54 @@ sw4b200_grid* sw4b200_grid_create( const sw4b200_grid_desc* desc )
 	 if( n > 0 )
 	 {
 	    g->nbf[s] = 3 * (size_t)n;
-	    if( !( g->bforce[s] = (double*)sw4b200_malloc( g->nbf[s] * 8 ) ) ) return 0;
+	    if( !( g->bforce[s] = (double*)sw4b200_malloc( g->nbf[s] * 8 ) ) ) return 1;
 	    cudaMemsetAsync( g->bforce[s], 0, g->nbf[s] * 8, g->st );
 	 }
       }
    }
-   for( int s = 0; s < 2; s++ )
-      if( !( g->halo_buf[s] = (double*)sw4b200_malloc( 6 * (size_t)g->b.nij * 8 ) ) ) return 0;
    cudaStreamSynchronize( g->st );
+   return 0;
+}
+
+sw4b200_grid* sw4b200_grid_create( const sw4b200_grid_desc* desc )
+{
+   if( need_init() ) return 0;
+   if( check_bounds( desc->ifirst, desc->ilast, desc->jfirst, desc->jlast, desc->kfirst, desc->klast ) ) return 0;
+   // a z-slab must own the SBP closure rows of its physical k-boundary and the planes they read (rhs4sg_rev.C:349-855:
+   // rows 1..6 read planes 0..8, rows nz-5..nz read planes nz-7..nz+1), and at least the two face planes per halo
+   {
+      const int own_lo = desc->kfirst + 2, own_hi = desc->klast - 2;
+      if( desc->halo_hi && desc->onesided[4] == 1 && own_hi < 8 )
+      {
+	 set_error( "grid_create: the slab [%d,%d] with the free surface must own the planes 1..8 of the closure rows", own_lo, own_hi );
+	 return 0;
+      }
+      if( desc->halo_lo && desc->onesided[5] == 1 && own_lo > desc->nz - 7 )
+      {
+	 set_error( "grid_create: the slab [%d,%d] with the lower SBP closure must own the planes nz-7..nz", own_lo, own_hi );
+	 return 0;
+      }
+      if( ( desc->halo_lo || desc->halo_hi ) && own_hi - own_lo + 1 < 4 )
+      {
+	 set_error( "grid_create: a z-slab needs at least 4 planes of its own (has %d)", own_hi - own_lo + 1 );
+	 return 0;
+      }
+   }
+   sw4b200_grid* g = new sw4b200_grid;
+   memset( g, 0, sizeof( *g ) );
+   g->d = *desc;
+   // (i,j,k,c) blocks with an odd number of points per row get their rows padded to an even pitch: 16-byte aligned rows are
+   // what the TMA-staged kernels need (tma.cuh), and the reference's own grids have odd ni (nx + 4 ghost points, EW.C:2057)
+   g->b = make_block( desc->corder, desc->ifirst, desc->ilast, desc->jfirst, desc->jlast, desc->kfirst, desc->klast, use_fast_path() );
+   g->st = g_streams[0];
+   g->fast = desc->corder == 1 && !desc->curvilinear && use_fast_path();
+   if( grid_alloc( g ) )
+   {
+      const std::string msg = g_err; // (grid_destroy does not overwrite it, but keep the first cause)
+      sw4b200_grid_destroy( g );
+      set_error( "%s", msg.c_str() );
+      return 0;
+   }
    return g;
 }
 
@@ -694,12 +779,12 @@ int sw4b200_grid_destroy( sw4b200_grid* g )
    if( !g ) return 0;
    cudaStreamSynchronize( g->st );
    double* ptrs[] = { g->U, g->Um, g->Up, g->Uacc, g->mu, g->la, g->rho, g->jac, g->met, g->d_f, g->d_rec,
-		      g->halo_buf[0], g->halo_buf[1], g->d_fser, g->d_fttser, g->d_recser, g->Lu };
+		      g->d_fser, g->d_fttser, g->d_recser, g->Lu };
    for( int d = 0; d < 3; d++ ) delete g->h_dc[d];
    delete g->sgd_boxes;
    delete g->sgd_zonly;
    for( double* p : ptrs ) if( p ) cudaFree( p );
-   for( int d = 0; d < 3; d++ ) { cudaFree( g->str[d] ); cudaFree( g->dc[d] ); cudaFree( g->co[d] ); }
+   for( int d = 0; d < 3; d++ ) { if( g->str[d] ) cudaFree( g->str[d] ); if( g->dc[d] ) cudaFree( g->dc[d] ); if( g->co[d] ) cudaFree( g->co[d] ); }
    for( int s = 0; s < 6; s++ ) if( g->bforce[s] ) cudaFree( g->bforce[s] );
    if( g->d_srcidx ) cudaFree( g->d_srcidx );
    if( g->d_recidx ) cudaFree( g->d_recidx );
@@ -712,10 +797,10 @@ int sw4b200_grid_destroy( sw4b200_grid* g )
 int sw4b200_grid_upload( sw4b200_grid* g, const char* name, const double* h_src )
 {
    size_t n = 0;
-   double** p = grid_array( g, name, &n );
+   int nc = 0;
+   double** p = grid_array( g, name, &n, &nc );
    if( !p || !*p ) return set_error( "grid_upload: unknown or unallocated array '%s'", name );
-   CUDA_OK( cudaMemcpyAsync( *p, h_src, n * 8, cudaMemcpyHostToDevice, g->st ) );
-   CUDA_OK( cudaStreamSynchronize( g->st ) );
+   if( grid_copy( g, *p, const_cast<double*>( h_src ), n, nc, true ) ) return 1;
    for( int d = 0; d < 3; d++ )
       if( p == &g->dc[d] )
       {
@@ -727,24 +812,26 @@ int sw4b200_grid_upload( sw4b200_grid* g, const char* name, const double* h_src 
 int sw4b200_grid_download( sw4b200_grid* g, const char* name, double* h_dst )
 {
    size_t n = 0;
-   double** p = grid_array( g, name, &n );
+   int nc = 0;
+   double** p = grid_array( g, name, &n, &nc );
    if( !p || !*p ) return set_error( "grid_download: unknown or unallocated array '%s'", name );
-   CUDA_OK( cudaMemcpyAsync( h_dst, *p, n * 8, cudaMemcpyDeviceToHost, g->st ) );
-   CUDA_OK( cudaStreamSynchronize( g->st ) );
-   return 0;
+   return grid_copy( g, *p, h_dst, n, nc, false );
 }
 void* sw4b200_grid_device_ptr( sw4b200_grid* g, const char* name )
 {
    size_t n = 0;
-   double** p = grid_array( g, name, &n );
+   int nc = 0;
+   double** p = grid_array( g, name, &n, &nc );
    return p ? (void*)*p : 0;
 }
 size_t sw4b200_grid_array_size( sw4b200_grid* g, const char* name )
 {
    size_t n = 0;
-   double** p = grid_array( g, name, &n );
+   int nc = 0;
+   double** p = grid_array( g, name, &n, &nc );
    return p ? n : 0;
 }
+int sw4b200_grid_row_pitch( sw4b200_grid* g ) { return g->b.ni; }
 
 static int set_points( sw4b200_grid* g, int n, const int* ijk, long long** d_idx )
 {
@@ -757,6 +844,14 @@ static int set_points( sw4b200_grid* g, int n, const int* ijk, long long** d_idx
       if( i < g->b.ifirst || i > g->b.ilast || j < g->b.jfirst || j > g->b.jlast || k < g->b.kfirst || k > g->b.klast )
 	 return set_error( "point (%d,%d,%d) is outside the block", i, j, k );
       idx[s] = pidx( g->b, i, j, k );
+   }
+   {
+      // the sparse kernels update one point per thread without atomics: the points must be distinct (EW::Force sums the
+      // sources that share a grid point before it adds them, EW.C:3092-3121 -- the caller does the same)
+      std::vector<long long> sorted( idx );
+      std::sort( sorted.begin(), sorted.end() );
+      for( int s = 1; s < n; s++ )
+	 if( sorted[s] == sorted[s - 1] ) return set_error( "set_points: two of the %d points share a grid point; merge them first", n );
    }
    CUDA_OK( cudaMalloc( (void**)d_idx, n * sizeof( long long ) ) );
    CUDA_OK( cudaMemcpy( *d_idx, idx.data(), n * sizeof( long long ), cudaMemcpyHostToDevice ) );
@@ -885,7 +980,7 @@ static void build_sgd_boxes( sw4b200_grid* g )
    g->sgd_boxes->clear();
    const int order = g->d.sg_order;
    const int w = order == 6 ? 3 : 2, hw = order == 6 ? 2 : 1;
-   const int n[3] = { g->b.ni, g->b.nj, g->b.nk };
+   const int n[3] = { g->b.nil, g->b.nj, g->b.nk };
    std::vector<std::pair<int, int>> on[3], off[3];
    for( int d = 0; d < 3; d++ )
    {
@@ -1180,8 +1275,9 @@ int sw4b200_grid_fetch_records( sw4b200_grid* g, int first_step, int nsteps, dou
 int sw4b200_grid_fill_profile( sw4b200_grid* g, const char* name, const double* h_kvalues )
 {
    size_t n = 0;
-   double** p = grid_array( g, name, &n );
-   if( !p || !*p || n != (size_t)g->b.npts ) return set_error( "grid_fill_profile: '%s' is not a scalar field of the block", name );
+   int nc = 0;
+   double** p = grid_array( g, name, &n, &nc );
+   if( !p || !*p || nc != 1 ) return set_error( "grid_fill_profile: '%s' is not a scalar field of the block", name );
    double* d_prof = 0;
    CUDA_OK( cudaMalloc( (void**)&d_prof, g->b.nk * sizeof( double ) ) );
    CUDA_OK( cudaMemcpy( d_prof, h_kvalues, g->b.nk * sizeof( double ), cudaMemcpyHostToDevice ) );

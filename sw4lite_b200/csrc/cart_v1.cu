@@ -374,7 +374,7 @@ __global__ void __launch_bounds__( CL_TX* CL_TY ) k_closure_staged( RhsArgs a, i
    }
    __syncthreads();
    const int li = li0 + tx, lj = lj0 + ty;
-   if( li > b.ni - 3 || lj > b.nj - 3 ) return;
+   if( li > b.nil - 3 || lj > b.nj - 3 ) return;
    Acc<MODE_LU> U = { sm, 0, 0, (long long)CL_NP * CL_PLANE, 1, 0.0 };
    const double* smu = sm + 3 * CL_NP * CL_PLANE;
    const double* sla = sm + 4 * CL_NP * CL_PLANE;
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__( CL_TX* CL_TY, 1 ) k_closure_fast( RhsArgs a, 
 	 }
       }
    }
-   if( !TMA && STAGED_OPS && li0 + tx <= b.ni - 3 && lj0 + ty <= b.nj - 3 )
+   if( !TMA && STAGED_OPS && li0 + tx <= b.nil - 3 && lj0 + ty <= b.nj - 3 )
    {
       // epilogue operands of the thread's own points: in flight together with the planes
       for( int kb = kb_lo; kb <= kb_hi; kb++ )
@@ -522,7 +522,7 @@ __global__ void __launch_bounds__( CL_TX* CL_TY, 1 ) k_closure_fast( RhsArgs a, 
    const double sgn = side == 0 ? 1.0 : -1.0;
    const int o = ( ty + 2 ) * PX + tx + 2;
    const int li = li0 + tx, lj = lj0 + ty;
-   const bool act = li <= b.ni - 3 && lj <= b.nj - 3;
+   const bool act = li <= b.nil - 3 && lj <= b.nj - 3;
    const double sx = s_sx[tx + 2], sy = s_sy[ty + 2];
    const double sxm2 = s_sx[tx], sxm1 = s_sx[tx + 1], sxp1 = s_sx[tx + 3], sxp2 = s_sx[tx + 4];
    const double sym2 = s_sy[ty], sym1 = s_sy[ty + 1], syp1 = s_sy[ty + 3], syp2 = s_sy[ty + 4];
@@ -714,8 +714,10 @@ template <int MODE>
 __global__ void k_shell_update( RhsArgs a )
 {
    const Block& b = a.b;
-   const long long nkplane = 2 * b.nij;				   // per k side
-   const long long njslab = 2LL * b.ni * ( b.nk - 4 );		   // per j side
+   const int nil = b.nil;					   // points per row (the row pitch b.ni may be one larger)
+   const long long nijl = (long long)nil * b.nj;
+   const long long nkplane = 2 * nijl;				   // per k side
+   const long long njslab = 2LL * nil * ( b.nk - 4 );		   // per j side
    const long long nislab = 2LL * ( b.nj - 4 ) * ( b.nk - 4 );	   // per i side
    const long long total = 2 * ( nkplane + njslab + nislab );
    for( long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
@@ -727,21 +729,21 @@ __global__ void k_shell_update( RhsArgs a )
       {
 	 const int side = s >= nkplane;
 	 s -= side * nkplane;
-	 k = (int)( s / b.nij );
-	 const long long rr = s % b.nij;
-	 j = (int)( rr / b.ni );
-	 i = (int)( rr % b.ni );
+	 k = (int)( s / nijl );
+	 const long long rr = s % nijl;
+	 j = (int)( rr / nil );
+	 i = (int)( rr % nil );
 	 if( side ) k += b.nk - 2;
       }
       else if( ( s -= 2 * nkplane ) < 2 * njslab )
       {
 	 const int side = s >= njslab;
 	 s -= side * njslab;
-	 const long long per_k = 2LL * b.ni;
+	 const long long per_k = 2LL * nil;
 	 k = 2 + (int)( s / per_k );
 	 const long long rr = s % per_k;
-	 j = (int)( rr / b.ni );
-	 i = (int)( rr % b.ni );
+	 j = (int)( rr / nil );
+	 i = (int)( rr % nil );
 	 if( side ) j += b.nj - 2;
       }
       else
@@ -754,12 +756,12 @@ __global__ void k_shell_update( RhsArgs a )
 	 const long long rr = s % per_k;
 	 j = 2 + (int)( rr / 2 );
 	 i = (int)( rr % 2 );
-	 if( side ) i += b.ni - 2;
+	 if( side ) i += nil - 2;
       }
       const long long p = (long long)i + (long long)b.ni * j + b.nij * k;
       if( MODE == MODE_SHELL_DPDMT )
       {
-	 const bool inner = i >= 2 && i < b.ni - 2 && j >= 2 && j < b.nj - 2;
+	 const bool inner = i >= 2 && i < nil - 2 && j >= 2 && j < b.nj - 2;
 	 if( inner && ( ( a.halo_lo && k < 2 ) || ( a.halo_hi && k >= b.nk - 2 ) ) ) continue;
 	 const double dt2i = 1.0 / ( a.dt * a.dt );
 #pragma unroll
@@ -898,7 +900,7 @@ __global__ void k_bc_freesurface( Block b, int k, int kl, double h, double* __re
 {
    const int ii = 2 + blockIdx.x * blockDim.x + threadIdx.x;
    const int jj = 2 + blockIdx.y * blockDim.y + threadIdx.y;
-   if( ii > b.ni - 3 || jj > b.nj - 3 ) return;
+   if( ii > b.nil - 3 || jj > b.nj - 3 ) return;
    const double d4a = 2.0 / 3.0, d4b = -1.0 / 12.0;
    const long long qq = (long long)ii + (long long)b.ni * jj;
    const long long p = qq + b.nij * ( k - b.kfirst );
@@ -920,7 +922,8 @@ __global__ void k_bc_freesurface( Block b, int k, int kl, double h, double* __re
    }
    const long long pg = p - b.nij * kl;
    const double m = mu[p], l = la[p];
-   const double b0 = bf ? bf[3 * qq] : 0.0, b1 = bf ? bf[3 * qq + 1] : 0.0, b2 = bf ? bf[3 * qq + 2] : 0.0;
+   const long long qb = (long long)ii + (long long)b.nil * jj; // the forcing array is indexed by window point (bcfortsg: qq)
+   const double b0 = bf ? bf[3 * qb] : 0.0, b1 = bf ? bf[3 * qb + 1] : 0.0, b2 = bf ? bf[3 * qb + 2] : 0.0;
    u[0 * sc + sp * pg] = ( -uz - kl * wx + kl * h * b0 / m ) / c_sbop[0];
    u[1 * sc + sp * pg] = ( -vz - kl * wy + kl * h * b1 / m ) / c_sbop[0];
    u[2 * sc + sp * pg] = ( -wz + ( -kl * l * ( ux + vy ) + kl * h * b2 ) / ( 2 * m + l ) ) / c_sbop[0];
@@ -1000,7 +1003,7 @@ static int launch_rows_general( RhsMode mode, const RhsArgs& a, int k_lo, int k_
    if( k_hi < k_lo ) return 0;
    ProfScope prof( "rhs_v1", st );
    dim3 bs( 32, 4, 2 );
-   dim3 gs( ( b.ni - 4 + bs.x - 1 ) / bs.x, ( b.nj - 4 + bs.y - 1 ) / bs.y, ( k_hi - k_lo + 1 + bs.z - 1 ) / bs.z );
+   dim3 gs( ( b.nil - 4 + bs.x - 1 ) / bs.x, ( b.nj - 4 + bs.y - 1 ) / bs.y, ( k_hi - k_lo + 1 + bs.z - 1 ) / bs.z );
    if( mode == MODE_LU ) k_rhs_v1<MODE_LU><<<gs, bs, 0, st>>>( a, k_lo, k_hi );
    else if( mode == MODE_PRED ) k_rhs_v1<MODE_PRED><<<gs, bs, 0, st>>>( a, k_lo, k_hi );
    else if( mode == MODE_CORR ) k_rhs_v1<MODE_CORR><<<gs, bs, 0, st>>>( a, k_lo, k_hi );
@@ -1038,7 +1041,7 @@ static int launch_closure_fast_tt( const RhsArgs& a, int side, int kb_lo, int kb
    const Block& b = a.b;
    ProfScope prof( "closure", st );
    dim3 bs( CL_TX, CL_TY, 1 );
-   dim3 gs( ( b.ni - 4 + CL_TX - 1 ) / CL_TX, ( b.nj - 4 + CL_TY - 1 ) / CL_TY, 1 );
+   dim3 gs( ( b.nil - 4 + CL_TX - 1 ) / CL_TX, ( b.nj - 4 + CL_TY - 1 ) / CL_TY, 1 );
    k_closure_fast<MODE, TMA><<<gs, bs, smem, st>>>( a, side, kb_lo, kb_hi, maps );
    count_launch();
    return check_launch( "k_closure_fast" );
@@ -1086,7 +1089,7 @@ static int launch_closure_t( const RhsArgs& a, int side, int kb_lo, int kb_hi, c
    const Block& b = a.b;
    ProfScope prof( "closure", st );
    dim3 bs( CL_TX, CL_TY, 1 );
-   dim3 gs( ( b.ni - 4 + CL_TX - 1 ) / CL_TX, ( b.nj - 4 + CL_TY - 1 ) / CL_TY, 1 );
+   dim3 gs( ( b.nil - 4 + CL_TX - 1 ) / CL_TX, ( b.nj - 4 + CL_TY - 1 ) / CL_TY, 1 );
    k_closure_staged<MODE><<<gs, bs, smem, st>>>( a, side, kb_lo, kb_hi );
    count_launch();
    return check_launch( "k_closure_staged" );
@@ -1105,7 +1108,7 @@ static int launch_closure( RhsMode mode, const RhsArgs& a, int side, int kb_lo, 
 int launch_rhs_v1_rows( RhsMode mode, const RhsArgs& a, int k_lo, int k_hi, cudaStream_t st )
 {
    const Block& b = a.b;
-   if( k_hi < k_lo || b.ni < 5 || b.nj < 5 ) return 0;
+   if( k_hi < k_lo || b.nil < 5 || b.nj < 5 ) return 0;
    int lo = k_lo, hi = k_hi;
    if( a.onesided4 && lo <= 6 && b.kfirst <= 0 && b.klast >= 8 && a.nk >= 12 )
    {
@@ -1131,7 +1134,7 @@ int launch_rhs_v1( RhsMode mode, const RhsArgs& a, cudaStream_t st )
 int launch_shell_update( RhsMode mode, const RhsArgs& a, cudaStream_t st )
 {
    const Block& b = a.b;
-   const long long total = 2 * ( 2 * b.nij + 2LL * b.ni * ( b.nk - 4 ) + 2LL * ( b.nj - 4 ) * ( b.nk - 4 ) );
+   const long long total = 2 * ( 2LL * b.nil * b.nj + 2LL * b.nil * ( b.nk - 4 ) + 2LL * ( b.nj - 4 ) * ( b.nk - 4 ) );
    ProfScope prof( "shell", st );
    if( mode == MODE_PRED ) k_shell_update<MODE_PRED><<<nblocks( total, 256 ), 256, 0, st>>>( a );
    else if( mode == MODE_SHELL_DPDMT ) k_shell_update<MODE_SHELL_DPDMT><<<nblocks( total, 256 ), 256, 0, st>>>( a );
@@ -1168,8 +1171,8 @@ int launch_addsgd( int order, const Block& b, double* up, const double* u, const
 {
    if( beta == 0 ) return 0;
    const int w = order == 6 ? 3 : 2;
-   if( b.ni <= 2 * w || b.nj <= 2 * w || b.nk <= 2 * w ) return 0;
-   Int6 box = { { w, b.ni - 1 - w, w, b.nj - 1 - w, w, b.nk - 1 - w } };
+   if( b.nil <= 2 * w || b.nj <= 2 * w || b.nk <= 2 * w ) return 0;
+   Int6 box = { { w, b.nil - 1 - w, w, b.nj - 1 - w, w, b.nk - 1 - w } };
    return launch_addsgd_box( order, b, box, up, u, um, rho, dcx, dcy, dcz, strx, stry, strz, cox, coy, coz, beta, st );
 }
 
@@ -1218,9 +1221,9 @@ int launch_bcfortsg( const Block& b, const Int36& wind, int nx, int ny, int nz, 
       {
 	 if( s != 4 && s != 5 )
 	    return set_error( "bcfortsg: free surface condition not implemented for side %d", s );
-	 if( b.ni < 5 || b.nj < 5 ) continue;
+	 if( b.nil < 5 || b.nj < 5 ) continue;
 	 dim3 bs( 32, 8 );
-	 dim3 gs( ( b.ni - 4 + 31 ) / 32, ( b.nj - 4 + 7 ) / 8 );
+	 dim3 gs( ( b.nil - 4 + 31 ) / 32, ( b.nj - 4 + 7 ) / 8 );
 	 k_bc_freesurface<<<gs, bs, 0, st>>>( b, s == 4 ? 1 : nz, s == 4 ? 1 : -1, h, u, mu, la, bforce.p[s], strx, stry );
 	 count_launch();
       }

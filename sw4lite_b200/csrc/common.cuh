@@ -21,16 +21,21 @@ __constant__ double c_sbop[5];
 struct Block
 {
    int ifirst, ilast, jfirst, jlast, kfirst, klast;
-   int ni, nj, nk;	 // allocated extents
-   long long nij, npts;	 // plane size, block size
+   int ni, nj, nk;	 // allocated extents (ni = row pitch in doubles)
+   int nil;		 // points per row, ilast-ifirst+1: ni, or ni-1 when the block's rows are padded to an even pitch
+			 // (grid blocks with odd ni: 16-byte aligned rows for the TMA-staged kernels); the pad column is
+			 // never written by a kernel and never read into a result
+   long long nij, npts;	 // plane size, block size (of the allocation)
    long long sc, sp;	 // component stride, point stride (corder=1: npts,1 ; corder=0: 1,3)
 };
 
-inline Block make_block( int corder, int ifirst, int ilast, int jfirst, int jlast, int kfirst, int klast )
+inline Block make_block( int corder, int ifirst, int ilast, int jfirst, int jlast, int kfirst, int klast, bool pad_even = false )
 {
    Block b;
    b.ifirst = ifirst; b.ilast = ilast; b.jfirst = jfirst; b.jlast = jlast; b.kfirst = kfirst; b.klast = klast;
    b.ni = ilast - ifirst + 1; b.nj = jlast - jfirst + 1; b.nk = klast - kfirst + 1;
+   b.nil = b.ni;
+   if( pad_even && corder && ( b.ni & 1 ) ) b.ni++;
    b.nij = (long long)b.ni * b.nj;
    b.npts = b.nij * b.nk;
    if( corder ) { b.sc = b.npts; b.sp = 1; }

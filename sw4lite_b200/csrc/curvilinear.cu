@@ -250,7 +250,7 @@ __global__ void __launch_bounds__( 128 ) k_rhs4sgcurv( CurvArgs a, int k_lo, int
    const int li = 2 + blockIdx.x * blockDim.x + threadIdx.x;
    const int lj = 2 + blockIdx.y * blockDim.y + threadIdx.y;
    const int k = k_lo + blockIdx.z * blockDim.z + threadIdx.z;
-   if( li > b.ni - 3 || lj > b.nj - 3 || k > k_hi ) return;
+   if( li > b.nil - 3 || lj > b.nj - 3 || k > k_hi ) return;
    const int lk = k - b.kfirst;
    const long long p = (long long)li + (long long)b.ni * lj + b.nij * lk;
    double r[3];
@@ -301,7 +301,7 @@ __global__ void k_addsgdc( int order, Block b, double* __restrict__ up, const do
    const int ii = w + blockIdx.x * blockDim.x + threadIdx.x;
    const int jj = w + blockIdx.y * blockDim.y + threadIdx.y;
    const int kk = w + blockIdx.z * blockDim.z + threadIdx.z;
-   if( ii > b.ni - 1 - w || jj > b.nj - 1 - w || kk > b.nk - 1 - w ) return;
+   if( ii > b.nil - 1 - w || jj > b.nj - 1 - w || kk > b.nk - 1 - w ) return;
    const long long p = (long long)ii + (long long)b.ni * jj + b.nij * kk;
    const double irhoj = beta / ( rho[p] * jac[p] );
    const double prex = strx[ii] * coy[jj], prey = stry[jj] * cox[ii];
@@ -321,7 +321,7 @@ __global__ void k_freesurfcurvisg( CurvArgs a, double* __restrict__ u, int k, in
    const Block& b = a.b;
    const int li = 2 + blockIdx.x * blockDim.x + threadIdx.x;
    const int lj = 2 + blockIdx.y * blockDim.y + threadIdx.y;
-   if( li > b.ni - 3 || lj > b.nj - 3 ) return;
+   if( li > b.nil - 3 || lj > b.nj - 3 ) return;
    const long long sc = b.sc, sp = b.sp, dj = b.ni, dk = b.nij;
    const double c1 = 2.0 / 3, c2 = -1.0 / 12;
    const long long qq = (long long)li + (long long)b.ni * lj;
@@ -336,7 +336,8 @@ __global__ void k_freesurfcurvisg( CurvArgs a, double* __restrict__ u, int k, in
    const double sx = a.strx[li], sy = a.stry[lj], isx = 1 / sx, isy = 1 / sy;
    const double dp0 = d0( 0, 1 ), dp1 = d0( 1, 1 ), dp2 = d0( 2, 1 );
    const double dq0 = d0( 0, dj ), dq1 = d0( 1, dj ), dq2 = d0( 2, dj );
-   const double f0 = forcing ? forcing[3 * qq] : 0.0, f1 = forcing ? forcing[3 * qq + 1] : 0.0, f2 = forcing ? forcing[3 * qq + 2] : 0.0;
+   const long long qb = (long long)li + (long long)b.nil * lj; // forcing(3,i,j) of the surface window
+   const double f0 = forcing ? forcing[3 * qb] : 0.0, f1 = forcing ? forcing[3 * qb + 1] : 0.0, f2 = forcing ? forcing[3 * qb + 2] : 0.0;
    // tangential part of the normal traction, divided by sx*sy (curvilinear-c.C:520-573)
    const double rhs1 = ( 2 * M + L ) * m2 * m1 * dp0 * sx * isy + M * m3 * m1 * dp1 + M * m4 * m1 * dp2 * isy +
 		       M * m3 * m1 * dq0 * isx * sy + L * m2 * m1 * dq1 - f0;
@@ -398,7 +399,7 @@ int launch_rhs4sgcurv( const Block& b, const double* u, const double* mu, const 
 		       const double* jac, double* lu, int onesided4, const double* strx, const double* stry,
 		       cudaStream_t st )
 {
-   if( b.ni < 5 || b.nj < 5 || b.nk < 5 ) return 0;
+   if( b.nil < 5 || b.nj < 5 || b.nk < 5 ) return 0;
    CurvArgs a;
    curv_args( a, b, u, mu, la, met, jac, lu, strx, stry );
    int kstart = b.kfirst + 2;
@@ -409,14 +410,14 @@ int launch_rhs4sgcurv( const Block& b, const double* u, const double* mu, const 
    {
       if( b.kfirst > 0 || b.klast < 8 )
 	 return set_error( "rhs4sgcurv: the free-surface closure needs planes 0..8 inside the block (k range %d:%d)", b.kfirst, b.klast );
-      dim3 gs( ( b.ni - 4 + bs.x - 1 ) / bs.x, ( b.nj - 4 + bs.y - 1 ) / bs.y, 6 );
+      dim3 gs( ( b.nil - 4 + bs.x - 1 ) / bs.x, ( b.nj - 4 + bs.y - 1 ) / bs.y, 6 );
       k_rhs4sgcurv<true><<<gs, bs, 0, st>>>( a, 1, 6 );
       count_launch();
       kstart = 7;
    }
    if( kend >= kstart )
    {
-      dim3 gs( ( b.ni - 4 + bs.x - 1 ) / bs.x, ( b.nj - 4 + bs.y - 1 ) / bs.y, kend - kstart + 1 );
+      dim3 gs( ( b.nil - 4 + bs.x - 1 ) / bs.x, ( b.nj - 4 + bs.y - 1 ) / bs.y, kend - kstart + 1 );
       k_rhs4sgcurv<false><<<gs, bs, 0, st>>>( a, kstart, kend );
       count_launch();
    }
@@ -429,10 +430,10 @@ int launch_addsgdc( int order, const Block& b, double* up, const double* u, cons
 {
    if( beta == 0 ) return 0;
    const int w = order == 6 ? 3 : 2;
-   if( b.ni <= 2 * w || b.nj <= 2 * w || b.nk <= 2 * w ) return 0;
+   if( b.nil <= 2 * w || b.nj <= 2 * w || b.nk <= 2 * w ) return 0;
    ProfScope prof( "addsgdc", st );
    dim3 bs( 32, 4, 2 );
-   dim3 gs( ( b.ni - 2 * w + bs.x - 1 ) / bs.x, ( b.nj - 2 * w + bs.y - 1 ) / bs.y, ( b.nk - 2 * w + bs.z - 1 ) / bs.z );
+   dim3 gs( ( b.nil - 2 * w + bs.x - 1 ) / bs.x, ( b.nj - 2 * w + bs.y - 1 ) / bs.y, ( b.nk - 2 * w + bs.z - 1 ) / bs.z );
    k_addsgdc<<<gs, bs, 0, st>>>( order, b, up, u, um, rho, dcx, dcy, strx, stry, jac, cox, coy, beta );
    count_launch();
    return check_launch( "k_addsgdc" );
@@ -443,11 +444,11 @@ int launch_freesurfcurvisg( const Block& b, int nz, int side, double* u, const d
 			    cudaStream_t st )
 {
    if( side != 5 && side != 6 ) return set_error( "freesurfcurvisg: side must be 5 (k=1) or 6 (k=nz)" );
-   if( b.ni < 5 || b.nj < 5 ) return 0;
+   if( b.nil < 5 || b.nj < 5 ) return 0;
    CurvArgs a;
    curv_args( a, b, u, mu, la, met, 0, 0, strx, stry );
    dim3 bs( 32, 8 );
-   dim3 gs( ( b.ni - 4 + 31 ) / 32, ( b.nj - 4 + 7 ) / 8 );
+   dim3 gs( ( b.nil - 4 + 31 ) / 32, ( b.nj - 4 + 7 ) / 8 );
    k_freesurfcurvisg<<<gs, bs, 0, st>>>( a, u, side == 5 ? 1 : nz, side == 5 ? 1 : -1, forcing );
    count_launch();
    return check_launch( "k_freesurfcurvisg" );
@@ -457,7 +458,7 @@ int launch_enforce_cart_topo( int corder, double* ucart, const Block& bc, double
 			      cudaStream_t st )
 {
    (void)corder;
-   if( bc.ni != bt.ni || bc.nj != bt.nj ) return set_error( "enforce_cart_topo: the two grids must share their i,j extents" );
+   if( bc.nil != bt.nil || bc.ni != bt.ni || bc.nj != bt.nj ) return set_error( "enforce_cart_topo: the two grids must share their i,j extents" );
    if( bt.nk < 5 || bc.nk < 5 ) return set_error( "enforce_cart_topo: grids too thin" );
    long long g = ( bc.nij + 255 ) / 256;
    if( g > 148 * 8 ) g = 148 * 8;

@@ -13,7 +13,7 @@
 //    predicated off), which lets ptxas interleave the independent in-plane and z-column work.
 //
 // Also compiled by g++ (SW4B200_EMULATE) for the CPU check of the kernel source (tests/emu).
-#include "common.cuh"
+#include "fast_common.cuh"
 
 namespace sw4b200 {
 
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__( 32 * TY, 1 ) k_rhs_fast2( const FastArgs a )
    }
    c.o = ( c.ty + 2 ) * PX + c.tx + 2; // own point in a staged plane
    const int li = li0 + c.tx, lj = lj0 + c.ty;
-   c.act = li <= b.ni - 3 && lj <= b.nj - 3;
+   c.act = li <= b.nil - 3 && lj <= b.nj - 3;
    c.gown = (long long)lj * b.ni + li; // own offset inside a plane (used only if act)
 
    fast2::State s;
@@ -419,7 +419,7 @@ int launch_fast2_t( const FastArgs& a, cudaStream_t st )
    }
    const Block& b = a.b;
    dim3 bs( C::TX, TY, 1 );
-   dim3 gs( ( b.ni - 4 + C::TX - 1 ) / C::TX, ( b.nj - 4 + TY - 1 ) / TY, ( a.khi - a.klo + 1 + a.kchunk - 1 ) / a.kchunk );
+   dim3 gs( ( b.nil - 4 + C::TX - 1 ) / C::TX, ( b.nj - 4 + TY - 1 ) / TY, ( a.khi - a.klo + 1 + a.kchunk - 1 ) / a.kchunk );
    ProfScope prof( EPI == EPI_PRED ? "rhs_fast_pred" : ( EPI == EPI_CORR ? "rhs_fast_corr" : "rhs_fast_lu" ), st );
    k_rhs_fast2<TY, EPI><<<gs, bs, smem, st>>>( a );
    count_launch();

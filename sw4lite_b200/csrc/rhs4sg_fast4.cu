@@ -1,7 +1,7 @@
 // Throughput path for the Cartesian interior rows, fourth generation (SoA layout, corder=1):
 // register blocking over x-pairs with the z state of both points in tensor memory.
 //
-// Same operator algebra and one-barrier-per-plane z-march as rhs4sg_fast2.cu / rhs4sg_fast3.cu (reference formulas
+// Same operator algebra and one-barrier-per-plane z-march as rhs4sg_fast2.cu (reference formulas
 // rhs4sg_rev.C:112-348 with the common subexpressions shared between threads).  ncu on those kernels
 // (profiles/r01c_fast3_ncu.md) showed a kernel that waits: issue slots 43 %, fp64 pipe 40 %, shared-memory pipe 67 %,
 // 8 warps per SM; a third of the instructions were integer/address work, and 12 warps only moved the stall to the
@@ -34,7 +34,8 @@
 //    0-11 g1A g1B g2A g2B g3A g3B | 12-39 pr0A pr0B pr1A pr1B pr2A pr2B e1A e1B e2A e2B e4A e4B e5A e5B
 //
 // Also compiled by g++ (SW4B200_EMULATE) for the CPU check of the kernel source (tests/emu).
-#include "common.cuh"
+#include "fast_common.cuh"
+#include "tmem.cuh"
 #include "tma.cuh"
 
 namespace sw4b200 {
@@ -52,9 +53,9 @@ using fast::W4;
 using fast::weights4;
 using fast::gsum;
 using fast::d0u;
-using fast3::Tm;
-using fast3::TmVal;
-using fast3::tm_get;
+using tmem::Tm;
+using tmem::TmVal;
+using tmem::tm_get;
 
 #if defined( SW4B200_EMULATE )
 struct D2 { double x, y; };
@@ -132,7 +133,9 @@ struct Ctx
    int li0, lj0; // local (array) index of the tile's first output
    int tid, txh, ty, o;
    int ka, kb, pend;
-   bool act; // the pair is inside the interior (ni is even and pairs start at even i: never split by the boundary)
+   bool act;  // the left point of the pair is inside the interior
+   bool act2; // SPLIT only (rows padded to an even pitch, odd number of points per row): the right point is inside too; without
+	      // padding pairs start at even i and the interior ends at an odd i, so a pair is never split by the boundary
    long long gown; // offset of the left point inside a plane
 };
 
@@ -191,7 +194,7 @@ __device__ __forceinline__ double pick( const D2& v, int t ) { return t ? v.y : 
 // One step of the march: plane p has been staged into ring slot S.  Does the in-plane work of plane p,
 // the z work of plane k=p-2 (publishing its exchanged products in E buffer S&1) and finishes plane k-1
 // (reading E buffer (S+1)&1).
-template <int TY, int EPI, int ORDER, int H>
+template <int TY, int EPI, int SPLIT, int H>
 __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, Ctx<TY>& c, State& s, Tm& tm, const int p, const Ph& ph )
 {
    typedef Cfg<TY> C;
@@ -279,12 +282,19 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
 	 // the pair is 16-byte aligned in global memory too (even ni, even li): one store per array
 	 if( fin )
 	 {
-	    st2( a.out[m] + qf, o1[0], o1[1] );
-	    if( EPI == EPI_PRED ) st2( a.out2[m] + qf, o2[0], o2[1] );
+	    if( SPLIT && !c.act2 )
+	    {
+	       a.out[m][qf] = o1[0];
+	       if( EPI == EPI_PRED ) a.out2[m][qf] = o2[0];
+	    }
+	    else
+	    {
+	       st2( a.out[m] + qf, o1[0], o1[1] );
+	       if( EPI == EPI_PRED ) st2( a.out2[m] + qf, o2[0], o2[1] );
+	    }
 	 }
       }
    };
-   if( ORDER == 1 ) finish(); // (warps 0-3: the load-heavy finish phase runs against the other warps' fp64-heavy in-plane phase)
    double g1n[2], g2n[2], g3n[2]; // g products of plane p
    // ---- in-plane pieces of plane p: an x pass and a y pass over the fields, so that only the weights of one
    // direction (2 points x 2 coefficient sets) are live next to the neighbours of one field
@@ -447,8 +457,7 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
 	 }
       }
       };
-   if( ORDER == 1 ) helper(); // (covers the tensor-memory loads)
-   if( ORDER == 0 ) finish();
+   finish();
    // ---- z pieces of plane k and its exchanged products
    double rnew[3][2];
    {
@@ -499,7 +508,7 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
       st2( ey + 2 * PY * TX, e6[0], e6[1] );
 
    }
-   if( ORDER == 0 ) helper();
+   helper();
 
 #pragma unroll
    for( int m = 0; m < 3; m++ ) { s.rp[m][0] = rnew[m][0]; s.rp[m][1] = rnew[m][1]; }
@@ -507,7 +516,7 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
 
 } // namespace fast4
 
-template <int TY, int EPI, int STAG>
+template <int TY, int EPI, int SPLIT>
 __global__ void __launch_bounds__( 16 * TY, 1 ) k_rhs_fast4( const FastArgs a, const SW4_GRID_CONSTANT FastMaps maps )
 {
    using namespace fast4;
@@ -575,7 +584,8 @@ __global__ void __launch_bounds__( 16 * TY, 1 ) k_rhs_fast4( const FastArgs a, c
    for( int t = c.tid; t < 6 * C::NH; t += NT ) smem[C::O_HML + t] = 0.0;
    c.o = ( c.ty + 2 ) * PX + 2 * c.txh + 2; // left own point in a staged plane
    const int li = li0 + 2 * c.txh, lj = lj0 + c.ty;
-   c.act = li + 1 <= b.ni - 3 && lj <= b.nj - 3;
+   c.act = li <= b.nil - 3 && lj <= b.nj - 3;
+   c.act2 = li + 1 <= b.nil - 3;
    c.gown = (long long)lj * b.ni + li;
 
    fast4::State s;
@@ -648,23 +658,18 @@ __global__ void __launch_bounds__( 16 * TY, 1 ) k_rhs_fast4( const FastArgs a, c
 	    s.amz[j][t] = s.amz[j + 2][t]; s.alz[j][t] = s.alz[j + 2][t];
 	 }
    };
-   // (STAG: the two warps of a scheduler (w, w+4) run the phases of a step in different orders)
-   const bool alt = STAG && c.tid < NT / 2;
    int p = c.ka - 2;
    if( p & 1 )
    {
-      if( alt ) fast4::step<TY, EPI, 1, 1>( a, maps, c, s, tm, p, ph );
-      else fast4::step<TY, EPI, 0, 1>( a, maps, c, s, tm, p, ph );
+      fast4::step<TY, EPI, SPLIT, 1>( a, maps, c, s, tm, p, ph );
       shift2(); next_plane(); p++;
    }
    while( p <= plast )
    {
-      if( alt ) fast4::step<TY, EPI, 1, 0>( a, maps, c, s, tm, p, ph );
-      else fast4::step<TY, EPI, 0, 0>( a, maps, c, s, tm, p, ph );
+      fast4::step<TY, EPI, SPLIT, 0>( a, maps, c, s, tm, p, ph );
       next_plane(); p++;
       if( p > plast ) break;
-      if( alt ) fast4::step<TY, EPI, 1, 1>( a, maps, c, s, tm, p, ph );
-      else fast4::step<TY, EPI, 0, 1>( a, maps, c, s, tm, p, ph );
+      fast4::step<TY, EPI, SPLIT, 1>( a, maps, c, s, tm, p, ph );
       shift2(); next_plane(); p++;
    }
 #if !defined( SW4B200_EMULATE )
@@ -677,7 +682,7 @@ __global__ void __launch_bounds__( 16 * TY, 1 ) k_rhs_fast4( const FastArgs a, c
 
 #ifndef SW4B200_EMULATE
 namespace {
-template <int TY, int EPI, int STAG>
+template <int TY, int EPI, int SPLIT>
 int launch_fast4_t( FastArgs a, cudaStream_t st )
 {
    typedef fast4::Cfg<TY> C;
@@ -685,7 +690,7 @@ int launch_fast4_t( FastArgs a, cudaStream_t st )
    const size_t smem = C::SMEM_DOUBLES * sizeof( double );
    if( !configured )
    {
-      cudaError_t e = cudaFuncSetAttribute( k_rhs_fast4<TY, EPI, STAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem );
+      cudaError_t e = cudaFuncSetAttribute( k_rhs_fast4<TY, EPI, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem );
       if( e != cudaSuccess ) return set_error( "k_rhs_fast4: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString( e ) );
       configured = true;
    }
@@ -704,9 +709,9 @@ int launch_fast4_t( FastArgs a, cudaStream_t st )
 	 if( make_tmap( &maps.um[f], a.um[f], b, C::TX, TY ) ) return 1;
    }
    dim3 bs( C::NT, 1, 1 );
-   dim3 gs( ( b.ni - 4 + C::TX - 1 ) / C::TX, ( b.nj - 4 + TY - 1 ) / TY, ( a.khi - a.klo + 1 + a.kchunk - 1 ) / a.kchunk );
+   dim3 gs( ( b.nil - 4 + C::TX - 1 ) / C::TX, ( b.nj - 4 + TY - 1 ) / TY, ( a.khi - a.klo + 1 + a.kchunk - 1 ) / a.kchunk );
    ProfScope prof( EPI == EPI_PRED ? "rhs_fast_pred" : ( EPI == EPI_CORR ? "rhs_fast_corr" : "rhs_fast_lu" ), st );
-   k_rhs_fast4<TY, EPI, STAG><<<gs, bs, smem, st>>>( a, maps );
+   k_rhs_fast4<TY, EPI, SPLIT><<<gs, bs, smem, st>>>( a, maps );
    count_launch();
    return check_launch( "k_rhs_fast4" );
 }
@@ -717,8 +722,9 @@ int launch_fast2( int epi, FastArgs a, cudaStream_t st );
 int launch_fast4( int epi, const FastArgs& a, cudaStream_t st )
 {
    if( a.khi < a.klo ) return 0;
-   // the row copies need 16-byte aligned rows: even ni and 16-byte aligned arrays.  The reference's own inputs give odd
-   // ni (205, 305, 605 + 4 ghost points ...): those grids take the cp.async kernel of the second generation.
+   // the tensor maps need 16-byte aligned rows: an even row pitch and 16-byte aligned arrays.  Caller-owned arrays with odd ni
+   // (the operator-level entry points on the reference's own layout) take the cp.async kernel of the second generation; grid
+   // blocks (sw4b200_grid_create) pad their rows to an even pitch and stay here.
    uintptr_t al = (uintptr_t)a.u[0] | (uintptr_t)a.u[1] | (uintptr_t)a.u[2] | (uintptr_t)a.mu | (uintptr_t)a.la;
    if( epi != EPI_LU ) al |= (uintptr_t)a.rho | (uintptr_t)a.um[0] | (uintptr_t)a.um[1] | (uintptr_t)a.um[2];
    al |= (uintptr_t)a.out[0] | (uintptr_t)a.out[1] | (uintptr_t)a.out[2];
@@ -729,16 +735,9 @@ int launch_fast4( int epi, const FastArgs& a, cudaStream_t st )
    // injected sparsely, pass A always stores uacc): the operator-level calls that use them take the cp.async kernel too
    if( epi != EPI_LU && a.fo[0] ) return launch_fast2( epi, a, st );
    if( epi == EPI_PRED && !a.out2[0] ) return launch_fast2( epi, a, st );
-   // SW4B200_F4_STAGGER=1: warps 0-3 run the phases of a step in another order than warps 4-7 (finish first), so that
-   // the two warps of a scheduler are in different phases.  Measured on B200: 19.9 ms against 19.0 ms per predictor
-   // pass -- off by default, kept for A/B runs.
-   static int stag = -1;
-   if( stag < 0 )
-   {
-      const char* e = getenv( "SW4B200_F4_STAGGER" );
-      stag = ( e && e[0] == '1' ) ? 1 : 0;
-   }
-   if( stag )
+   // grid blocks with an odd number of points per row are allocated with rows padded to an even pitch (api.cu): the last pair of
+   // a row is then split by the boundary (SPLIT variant: that pair stores its left point only)
+   if( a.b.nil != a.b.ni )
       switch( epi )
       {
       case EPI_LU: return launch_fast4_t<16, EPI_LU, 1>( a, st );

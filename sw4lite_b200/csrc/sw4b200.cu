@@ -1,8 +1,6 @@
 // Single translation unit of libsw4b200.so (constant-memory tables are shared by all kernels).
 #include "cart_v1.cu"
-#include "rhs4sg_fast.cu"
 #include "rhs4sg_fast2.cu"
-#include "rhs4sg_fast3.cu"
 #include "rhs4sg_fast4.cu"
 #include "addsgd_fast.cu"
 #include "curvilinear.cu"

@@ -70,6 +70,7 @@ SIGNATURES = {
     "sw4b200_grid_download": (I, [VP, C.c_char_p, c_dp]),
     "sw4b200_grid_device_ptr": (VP, [VP, C.c_char_p]),
     "sw4b200_grid_array_size": (C.c_size_t, [VP, C.c_char_p]),
+    "sw4b200_grid_row_pitch": (I, [VP]),
     "sw4b200_grid_set_source_points": (I, [VP, I, c_ip]),
     "sw4b200_grid_set_receiver_points": (I, [VP, I, c_ip]),
     "sw4b200_grid_predictor": (I, [VP, c_dp]),

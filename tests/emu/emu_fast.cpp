@@ -1,4 +1,4 @@
-// TEST INFRASTRUCTURE ONLY: runs sw4lite_b200/csrc/rhs4sg_fast.cu's kernel on the CPU through
+// TEST INFRASTRUCTURE ONLY: runs the kernels of sw4lite_b200/csrc/rhs4sg_fast2.cu and rhs4sg_fast4.cu on the CPU through
 // tests/emu/cuda_emu.h.  extern "C" entry for ctypes (tests/test_emu_fast.py).
 #include "cuda_emu.h"
 namespace emu {
@@ -7,32 +7,21 @@ dim3 g_blockIdx, g_blockDim, g_gridDim;
 double* g_smem = 0;
 std::barrier<>* g_barrier = 0;
 }
-#include "../../sw4lite_b200/csrc/rhs4sg_fast.cu"
 #include "../../sw4lite_b200/csrc/rhs4sg_fast2.cu"
-#include "../../sw4lite_b200/csrc/rhs4sg_fast3.cu"
 #include "../../sw4lite_b200/csrc/rhs4sg_fast4.cu"
 
 using namespace sw4b200;
 
-// third generation: gen = 3000 + 10*TY + TMODE
-template <int TY, int TMODE>
-static void run_fast3( int epi, const FastArgs& a )
-{
-   typedef fast3::Cfg<TY> C3;
-   dim3 bs( C3::TX, TY, 1 );
-   dim3 gs( ( a.b.ni - 4 + C3::TX - 1 ) / C3::TX, ( a.b.nj - 4 + TY - 1 ) / TY, ( a.khi - a.klo + 1 + a.kchunk - 1 ) / a.kchunk );
-   if( epi == EPI_LU ) emu::launch( gs, bs, C3::SMEM_DOUBLES, [&]() { k_rhs_fast3<TY, EPI_LU, TMODE>( a ); } );
-   else if( epi == EPI_PRED ) emu::launch( gs, bs, C3::SMEM_DOUBLES, [&]() { k_rhs_fast3<TY, EPI_PRED, TMODE>( a ); } );
-   else emu::launch( gs, bs, C3::SMEM_DOUBLES, [&]() { k_rhs_fast3<TY, EPI_CORR, TMODE>( a ); } );
-}
-
-extern "C" int emu_rhs_fast( int gen, int epi, int ifirst, int ilast, int jfirst, int jlast, int kfirst, int klast, int klo, int khi,
-			     int kchunk, const double* u, const double* mu, const double* la, const double* strx,
+// gen 4: rhs4sg_fast4.cu (the product configuration; the SPLIT variant when pitch > ni), gen 2: rhs4sg_fast2.cu.
+// pitch = row pitch of the arrays in doubles (ni, or ni+1 for a block whose odd rows are padded to an even pitch)
+extern "C" int emu_rhs_fast( int gen, int epi, int ifirst, int ilast, int jfirst, int jlast, int kfirst, int klast, int pitch, int klo,
+			     int khi, int kchunk, const double* u, const double* mu, const double* la, const double* strx,
 			     const double* stry, const double* strz, double cof, double* out, double* out2,
 			     const double* um, const double* rho, const double* fo, double fac )
 {
    FastArgs a;
-   a.b = make_block( 1, ifirst, ilast, jfirst, jlast, kfirst, klast );
+   a.b = make_block( 1, ifirst, ilast, jfirst, jlast, kfirst, klast, pitch > ilast - ifirst + 1 );
+   if( a.b.ni != pitch ) return 1;
    a.klo = klo; a.khi = khi; a.kchunk = kchunk;
    const long long n = a.b.npts;
    for( int c = 0; c < 3; c++ )
@@ -44,16 +33,16 @@ extern "C" int emu_rhs_fast( int gen, int epi, int ifirst, int ilast, int jfirst
       a.fo[c] = fo ? fo + c * n : 0;
    }
    a.mu = mu; a.la = la; a.strx = strx; a.stry = stry; a.strz = strz; a.cof6 = cof / 6; a.cof144 = cof / 144; a.rho = rho; a.fac = fac;
-   if( gen == 4 || gen == 41 ) // 4: the product configuration; 41: staggered phase order (A/B variant)
+   if( gen == 4 )
    {
       constexpr int TY4 = 16;
       typedef fast4::Cfg<TY4> C4;
       dim3 bs( C4::NT, 1, 1 );
-      dim3 gs( ( a.b.ni - 4 + C4::TX - 1 ) / C4::TX, ( a.b.nj - 4 + TY4 - 1 ) / TY4, ( khi - klo + 1 + kchunk - 1 ) / kchunk );
+      dim3 gs( ( a.b.nil - 4 + C4::TX - 1 ) / C4::TX, ( a.b.nj - 4 + TY4 - 1 ) / TY4, ( khi - klo + 1 + kchunk - 1 ) / kchunk );
       FastMaps maps; // (the emulated TMA tile load reads through the array base)
       for( int c = 0; c < 3; c++ ) { maps.u[c].base = a.u[c]; maps.um[c].base = a.um[c]; }
       maps.mu.base = a.mu; maps.la.base = a.la; maps.rho.base = a.rho;
-      if( gen == 4 )
+      if( a.b.nil == a.b.ni )
       {
 	 if( epi == EPI_LU ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_LU, 0>( a, maps ); } );
 	 else if( epi == EPI_PRED ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_PRED, 0>( a, maps ); } );
@@ -67,31 +56,12 @@ extern "C" int emu_rhs_fast( int gen, int epi, int ifirst, int ilast, int jfirst
       }
       return 0;
    }
-   if( gen >= 3000 )
-   {
-      switch( gen - 3000 )
-      {
-      case 81: run_fast3<8, 1>( epi, a ); break;
-      case 82: run_fast3<8, 2>( epi, a ); break;
-      case 121: run_fast3<12, 1>( epi, a ); break;
-      default: run_fast3<12, 2>( epi, a ); break;
-      }
-      return 0;
-   }
    constexpr int TY = 8;
-   typedef fast::Cfg<TY> C;
-   dim3 bs( C::TX, TY, 1 );
-   dim3 gs( ( a.b.ni - 4 + C::TX - 1 ) / C::TX, ( a.b.nj - 4 + TY - 1 ) / TY, ( khi - klo + 1 + kchunk - 1 ) / kchunk );
-   if( gen == 2 )
-   {
-      typedef fast2::Cfg<TY> C2;
-      if( epi == EPI_LU ) emu::launch( gs, bs, C2::SMEM_DOUBLES, [&]() { k_rhs_fast2<TY, EPI_LU>( a ); } );
-      else if( epi == EPI_PRED ) emu::launch( gs, bs, C2::SMEM_DOUBLES, [&]() { k_rhs_fast2<TY, EPI_PRED>( a ); } );
-      else emu::launch( gs, bs, C2::SMEM_DOUBLES, [&]() { k_rhs_fast2<TY, EPI_CORR>( a ); } );
-      return 0;
-   }
-   if( epi == EPI_LU ) emu::launch( gs, bs, C::SMEM_DOUBLES, [&]() { k_rhs_fast<TY, EPI_LU>( a ); } );
-   else if( epi == EPI_PRED ) emu::launch( gs, bs, C::SMEM_DOUBLES, [&]() { k_rhs_fast<TY, EPI_PRED>( a ); } );
-   else emu::launch( gs, bs, C::SMEM_DOUBLES, [&]() { k_rhs_fast<TY, EPI_CORR>( a ); } );
+   typedef fast2::Cfg<TY> C2;
+   dim3 bs( C2::TX, TY, 1 );
+   dim3 gs( ( a.b.nil - 4 + C2::TX - 1 ) / C2::TX, ( a.b.nj - 4 + TY - 1 ) / TY, ( khi - klo + 1 + kchunk - 1 ) / kchunk );
+   if( epi == EPI_LU ) emu::launch( gs, bs, C2::SMEM_DOUBLES, [&]() { k_rhs_fast2<TY, EPI_LU>( a ); } );
+   else if( epi == EPI_PRED ) emu::launch( gs, bs, C2::SMEM_DOUBLES, [&]() { k_rhs_fast2<TY, EPI_PRED>( a ); } );
+   else emu::launch( gs, bs, C2::SMEM_DOUBLES, [&]() { k_rhs_fast2<TY, EPI_CORR>( a ); } );
    return 0;
 }

@@ -1,5 +1,5 @@
-"""CPU test of the fast interior kernel's algebra and index logic: the CUDA source of
-sw4lite_b200/csrc/rhs4sg_fast.cu compiled by g++ through tests/emu/cuda_emu.h (one OS thread per
+"""CPU test of the fast interior kernels' algebra and index logic: the CUDA source of
+sw4lite_b200/csrc/rhs4sg_fast2.cu and rhs4sg_fast4.cu compiled by g++ through tests/emu/cuda_emu.h (one OS thread per
 CUDA thread) against the oracle.  This is test infrastructure for the kernel source, not a product
 path: the library itself has no CPU implementation."""
 import ctypes as C
@@ -15,19 +15,21 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 EMU = os.path.join(HERE, "emu")
 LIB = os.path.join(EMU, "libemu_fast.so")
 SRC = [os.path.join(EMU, "emu_fast.cpp"), os.path.join(EMU, "cuda_emu.h"),
-       os.path.join(HERE, "..", "sw4lite_b200", "csrc", "rhs4sg_fast.cu"),
        os.path.join(HERE, "..", "sw4lite_b200", "csrc", "rhs4sg_fast2.cu"),
-       os.path.join(HERE, "..", "sw4lite_b200", "csrc", "rhs4sg_fast3.cu"),
        os.path.join(HERE, "..", "sw4lite_b200", "csrc", "rhs4sg_fast4.cu"),
+       os.path.join(HERE, "..", "sw4lite_b200", "csrc", "fast_common.cuh"),
+       os.path.join(HERE, "..", "sw4lite_b200", "csrc", "tmem.cuh"),
+       os.path.join(HERE, "..", "sw4lite_b200", "csrc", "tma.cuh"),
        os.path.join(HERE, "..", "sw4lite_b200", "csrc", "common.cuh")]
 _dp = C.POINTER(C.c_double)
 GEN = 2  # generation of the fast kernel under test, set per test by the fixture below
 
 
-@pytest.fixture(autouse=True, params=[4, 2, 3122, 3082], ids=["fast4-pairs", "fast2", "fast3-12w-tm2", "fast3-8w-tm2"])
+@pytest.fixture(autouse=True, params=[4, 40, 2], ids=["fast4-pairs", "fast4-padded-rows", "fast2"])
 def generation(request):
     """4: rhs4sg_fast4.cu (x-pair register blocking, z state in tensor memory -- emulated here as a per-thread
-    array); 2: rhs4sg_fast2.cu; 3000+10*TY+TMODE: rhs4sg_fast3.cu"""
+    array) on a grid with even ni; 40: the same kernel on a grid with ODD ni whose rows are padded to an even pitch
+    (what sw4b200_grid_create does; the pad column holds NaN here: it must never reach a result); 2: rhs4sg_fast2.cu"""
     global GEN
     GEN = request.param
     yield
@@ -39,7 +41,8 @@ def emu():
         subprocess.check_call(["/usr/bin/g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-DSW4B200_EMULATE",
                                "-ffp-contract=off", "-o", LIB, SRC[0]])
     lib = C.CDLL(LIB)
-    lib.emu_rhs_fast.argtypes = [C.c_int] * 11 + [_dp] * 6 + [C.c_double] + [_dp] * 5 + [C.c_double]
+    lib.emu_rhs_fast.argtypes = [C.c_int] * 12 + [_dp] * 6 + [C.c_double] + [_dp] * 5 + [C.c_double]
+    lib.emu_rhs_fast.restype = C.c_int
     return lib
 
 
@@ -50,12 +53,41 @@ def d(a):
 def even(dims):
     """the fourth generation stages rows with 16-byte bulk copies: ni (= nx + 4 ghost points) must be even; odd
     grids are served by the second generation (launch_fast4 dispatches)"""
-    return ((dims[0] + 1) // 2 * 2,) + tuple(dims[1:]) if GEN == 4 else dims
+    if GEN == 4:
+        return ((dims[0] + 1) // 2 * 2,) + tuple(dims[1:])
+    if GEN == 40:
+        return (dims[0] // 2 * 2 + 1,) + tuple(dims[1:])
+    return dims
+
+
+def _pad(a, box, fill=np.nan):
+    """rows of ni values -> rows of ni+1 values (row pitch of a padded block)"""
+    if a is None:
+        return None
+    r = a.reshape(-1, box.ni)
+    return np.ascontiguousarray(np.concatenate([r, np.full((r.shape[0], 1), fill)], axis=1)).ravel()
 
 
 def run(emu, epi, box, klo, khi, kchunk, f, cof, out, out2=None, um=None, rho=None, fo=None, fac=0.0):
-    emu.emu_rhs_fast(GEN, epi, *box.bounds, klo, khi, kchunk, d(f["u"]), d(f["mu"]), d(f["la"]), d(f["strx"]), d(f["stry"]),
-                     d(f["strz"]), cof, d(out), d(out2), d(um), d(rho), d(fo), fac)
+    if GEN != 40:
+        rc = emu.emu_rhs_fast(GEN, epi, *box.bounds, box.ni, klo, khi, kchunk, d(f["u"]), d(f["mu"]), d(f["la"]), d(f["strx"]),
+                              d(f["stry"]), d(f["strz"]), cof, d(out), d(out2), d(um), d(rho), d(fo), fac)
+        assert rc == 0
+        return
+    assert box.ni % 2 == 1
+    SENT = 7.25
+    inplace = um is out
+    pout = _pad(out, box, SENT); pout2 = _pad(out2, box, SENT)
+    pum = pout if inplace else _pad(um, box)
+    rc = emu.emu_rhs_fast(4, epi, *box.bounds, box.ni + 1, klo, khi, kchunk, d(_pad(f["u"], box)), d(_pad(f["mu"], box)),
+                          d(_pad(f["la"], box)), d(np.append(f["strx"], np.nan)), d(f["stry"]), d(f["strz"]), cof, d(pout), d(pout2),
+                          d(pum), d(_pad(rho, box)), d(_pad(fo, box)), fac)
+    assert rc == 0
+    for dst, src in ((out, pout), (out2, pout2)):
+        if dst is not None:
+            r = src.reshape(-1, box.ni + 1)
+            assert np.all(r[:, -1] == SENT)           # the pad column is never written
+            dst[:] = r[:, :-1].ravel()
 
 
 def cpu_lu(box, f, h, onesided=(0,) * 6, nk=None):
@@ -113,14 +145,14 @@ def test_emu_predictor_and_corrector_epilogues(emu):
     box = Box(*even((41, 19, 15)))
     f = random_fields(box, seed=23)
     h, dt = 0.4, 0.05
-    if GEN == 4:      # dense forcing is not on the fourth generation's path (launch_fast4 sends it to the second)
+    if GEN in (4, 40):      # dense forcing is not on the fourth generation's path (launch_fast4 sends it to the second)
         f["fo"] = np.zeros_like(f["fo"])
     O = oracle()
     lu = cpu_lu(box, f, h)
     up = np.zeros(3 * box.npts)
     O.predfort(1, box.bounds, up, f["u"], f["um"], lu, f["fo"], f["rho"], dt * dt)
     out = np.zeros(3 * box.npts); out2 = np.zeros(3 * box.npts)
-    run(emu, 1, box, box.kfirst + 2, box.klast - 2, 6, f, 1 / h ** 2, out, out2=out2, um=f["um"], rho=f["rho"], fo=None if GEN == 4 else f["fo"], fac=dt * dt)
+    run(emu, 1, box, box.kfirst + 2, box.klast - 2, 6, f, 1 / h ** 2, out, out2=out2, um=f["um"], rho=f["rho"], fo=None if GEN in (4, 40) else f["fo"], fac=dt * dt)
     inner = (slice(None), slice(2, -2), slice(2, -2), slice(2, -2))
     r4 = lambda x: x.reshape(3, box.nk, box.nj, box.ni)
     assert relerr(r4(out)[inner], r4(up)[inner]) < 1e-13
@@ -130,5 +162,5 @@ def test_emu_predictor_and_corrector_epilogues(emu):
     ref = f["up"].copy()
     O.corrfort(1, box.bounds, ref, lu, f["fo"], f["rho"], dt ** 4)
     out = f["up"].copy()
-    run(emu, 2, box, box.kfirst + 2, box.klast - 2, 6, f, 1 / h ** 2, out, um=out, rho=f["rho"], fo=None if GEN == 4 else f["fo"], fac=dt ** 4 / 12)
+    run(emu, 2, box, box.kfirst + 2, box.klast - 2, 6, f, 1 / h ** 2, out, um=out, rho=f["rho"], fo=None if GEN in (4, 40) else f["fo"], fac=dt ** 4 / 12)
     assert relerr(r4(out)[inner], r4(ref)[inner]) < 1e-13
