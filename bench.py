@@ -3,8 +3,10 @@
 hot path: fused rhs4sg+predictor, rhs4sg+corrector, supergrid damping, boundary conditions, halo
 exchange) on a synthetic half-space, z-slab decomposed over the GPUs of one node.
 
-  python bench.py [--gpus N --steps K --warmup W]            our CUDA path (one rank per GPU)
-  python bench.py --impl reference [--steps K --warmup W]    the reference CPU (C/OpenMP) path
+  python bench.py [--gpus N --steps K --warmup W]                 our CUDA path (one rank per GPU)
+  python bench.py --impl reference [--steps K --warmup W]         the reference CPU (C/OpenMP) path, all host threads
+  python bench.py --impl reference-cuda                           the reference's OWN CUDA path on this GPU (timing only)
+  python bench.py --config strong|testil256|host ...              the other BASELINE.json configurations (see parse())
 
 One step = one full time step of the whole grid (EW::timesteploop body, reference EW.C:2527-2842).
 One grid-point update = one interior grid point advanced by one time step.  Workload per GPU:
@@ -36,7 +38,14 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
+    ap.add_argument("--config", default="sweep", choices=["sweep", "strong", "testil256", "host"],
+                    help="sweep: weak-scaling sweep, nx x ny x nzl per GPU (BASELINE.json config 5, the default line); strong: nx x ny x "
+                         "nz-total split over the GPUs (config 5, strong scaling); testil256: standalone rhs4sg on the reference "
+                         "harness's 256^3 fields (config 2); host: the reference's own program (main, parser, set-up) on this "
+                         "repository's kernels, host/_build/sw4lite_b200, on a generated .in file")
+    ap.add_argument("--nz-total", type=int, default=256, help="--config strong: interior planes of the whole grid")
+    ap.add_argument("--host-grid", default="640x640x320", help="grid of --config host and --impl reference-cuda")
     ap.add_argument("--nx", type=int, default=2048)
     ap.add_argument("--ny", type=int, default=2048)
     ap.add_argument("--nzl", type=int, default=128, help="interior planes per GPU (weak scaling)")
@@ -134,6 +143,12 @@ def time_reference(grid, steps, warmup):
         raise RuntimeError("oracle/_ref/libsw4ref.so is not built")
     nx, ny, nz = [int(x) for x in grid.split("x")]
     os.environ.setdefault("OMP_PROC_BIND", "spread")
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers)
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except Exception:
+        ncores = os.cpu_count() or 1
+    refshim.set_num_threads(int(os.environ.get("SW4B200_REF_THREADS", ncores)))
     with tempfile.TemporaryDirectory() as tmp, quiet_stdout():
         ew = refshim.RefEW(ref_input(tmp, nx, ny, nz, 10.0, steps + warmup), tmp)
         for _ in range(warmup):
@@ -151,23 +166,116 @@ def main_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = min(a.steps, 10)
-    warmup = min(a.warmup, 2)
+    steps, warmup = a.steps, a.warmup
     g, ms, threads, sample = time_reference(a.cpu_grid, steps, warmup)
+    cfg = workload_config(a, a.gpus)
+    cfg["workload"] = ("CPU sample %s of: " % a.cpu_grid) + cfg["workload"]
+    cfg["grid_timed"] = [int(x) for x in a.cpu_grid.split("x")]
+    cfg["stepping"] = ("the reference's kernels and order of operations (EW.C:2527-2763) driven step by step through oracle/ref_shim.C "
+                       "(the reference's timesteploop symbol is weakened in libsw4ref.so); sequencing pinned by the golden pointsource line")
     line = {"impl": "reference", "metric": "grid-point updates/sec per timestep", "value": g, "unit": "Gpts/s",
             "n_gpus": a.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(a, a.gpus),
+            "config": cfg,
             "cpu_baseline": {"value": g, "unit": "Gpts/s", "cores": threads, "kind": "reference", "sample": sample},
             "e2e": {"value": g, "unit": "Gpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
+def host_input(path, nx, ny, nz, h, steps):
+    """the bench workload's pattern (tests/cartesian/basic.in) as a .in file for the reference's own main(): timing on"""
+    txt = "\n".join([
+        "fileio path=%s verbose=0" % os.path.join(path, "out"),
+        "grid nx=%d ny=%d nz=%d h=%g" % (nx, ny, nz, h),
+        "time steps=%d" % steps,
+        "developer checkfornan=0 reporttiming=1 corder=1 cfl=1.3",
+        "supergrid gp=30",
+        "block vp=4000 vs=2000 r=2600",
+        "block vp=6000 vs=3464 r=2700 z1=%g" % (0.6 * nz * h),
+        "source x=%g y=%g z=%g mxy=1e18 t0=0 freq=10 type=C6SmoothBump" % (0.5 * nx * h, 0.5 * ny * h, 0.3 * nz * h),
+        "rec x=%g y=%g depth=0 file=sta01 usgsformat=1 sacformat=0" % (0.4 * nx * h, 0.3 * ny * h), ""])
+    f = os.path.join(path, "bench.in")
+    open(f, "w").write(txt)
+    return f
+
+
+def run_program(exe, grid, steps):
+    """run a build of the reference's program (its own CUDA build, or its host linked to libsw4b200.so) on the generated input
+    and read its own timers (`developer reporttiming=1`, EW.C:2863-2882: the summary skips the first step).
+    Returns dict(gpts, ms_per_step, total_s, solver_s, columns)"""
+    nx, ny, nz = [int(x) for x in grid.split("x")]
+    with tempfile.TemporaryDirectory() as tmp:
+        inp = host_input(tmp, nx, ny, nz, 10.0, steps)
+        t0 = time.perf_counter()
+        r = subprocess.run([exe, inp], cwd=tmp, capture_output=True, text=True, timeout=3000)
+        wall = time.perf_counter() - t0
+    if r.returncode != 0:
+        raise RuntimeError("%s failed: %s" % (exe, (r.stdout + r.stderr)[-1500:]))
+    lines = r.stdout.splitlines()
+    cols = None
+    for n, l in enumerate(lines):
+        if l.strip().startswith("Total") and "Scheme" in l and n + 1 < len(lines):
+            cols = [float(x) for x in lines[n + 1].split()]
+    solver = [l for l in lines if "Execution time, solver phase" in l]
+    if not cols:
+        raise RuntimeError("no timing summary in the output of %s: %s" % (exe, r.stdout[-1500:]))
+    total = cols[0]
+    names = ["total", "bc_comm", "bc_phys", "scheme", "supergrid", "forcing"]
+    return {"gpts": nx * ny * nz * (steps - 1) / total / 1e9, "ms_per_step": 1e3 * total / (steps - 1), "total_s": total,
+            "solver_phase": solver[-1].strip() if solver else None, "columns": dict(zip(names, cols)), "wall_s": wall,
+            "devices_line": next((l.strip() for l in lines if "CUDA device" in l or "Cuda devices" in l), None)}
+
+
+REF_CUDA_EXE = os.path.join(ROOT, "oracle", "_ref", "cuda", "sw4lite_ref_cuda")
+HOST_EXE = os.path.join(ROOT, "host", "_build", "sw4lite_b200")
+
+
+def program_line(a, impl, exe, what):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(a.steps + 1, 3)
+    nx, ny, nz = [int(x) for x in a.host_grid.split("x")]
+    base = {"impl": impl, "metric": "grid-point updates/sec per timestep", "unit": "Gpts/s", "n_gpus": 1, "steps": steps - 1,
+            "warmup": 1, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic Cartesian half-space %s, free surface + supergrid gp=30, two material blocks, one "
+                                   "moment source, one receiver, corder=1: %s; timed by the program's own `developer reporttiming=1` "
+                                   "summary (all steps but the first)" % (a.host_grid, what), "grid": [nx, ny, nz]}}
+    if not os.path.exists(exe):
+        base.update({"unavailable": "%s is not built (needs /root/reference at build time)" % os.path.relpath(exe, ROOT)})
+        print(json.dumps(base))
+        return
+    try:
+        r = run_program(exe, a.host_grid, steps)
+    except Exception as e:
+        base.update({"unavailable": "run failed: %s" % str(e)[-400:]})
+        print(json.dumps(base))
+        return
+    base.update({"value": r["gpts"], "ms_per_step": r["ms_per_step"], "program_timers_s": r["columns"], "solver_phase": r["solver_phase"],
+                 "wall_s": r["wall_s"], "devices": r["devices_line"],
+                 "e2e": {"value": r["gpts"], "unit": "Gpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 24,
+                         "note": "the program's own time loop: wavefield device resident, one receiver sample to the host per step"},
+                 "step_frac_of_hbm": BYTES_PER_POINT_STEP * r["gpts"] / peaks()[0]})
+    print(json.dumps(base))
+
+
+def main_reference_cuda(a):
+    """the reference's own CUDA program (EW_cuda.C / device-routines.C, built unmodified for sm_100 by oracle/build_ref_cuda.py)"""
+    program_line(a, "reference-cuda", REF_CUDA_EXE,
+                 "the UNMODIFIED reference CUDA build (Makefile.cuda recipe, -arch=sm_100; rhs4_v2 & co., device-routines.C:9992)")
+
+
+def main_host(a):
+    """the reference's own main()/parser/set-up/time loop linked against libsw4b200.so (host/EW_cuda_b200.C)"""
+    program_line(a, "ours-host", HOST_EXE,
+                 "the reference's own host program (main, .in parser, set-up, EW::timesteploop) on libsw4b200.so through host/EW_cuda_b200.C")
+
+
 def workload_config(a, n):
-    return {"workload": "synthetic Cartesian half-space %dx%dx%d (z-slabs of %d planes per GPU), free surface + supergrid gp=30, "
+    return {"workload": "synthetic Cartesian half-space %dx%dx%d (z-slabs of %d planes per GPU%s), free surface + supergrid gp=30, "
                         "216-point source, 64 surface receivers; full time step (fused rhs4sg+predictor, rhs4sg+corrector, addsgd4, "
-                        "bcfortsg, halo exchange)" % (a.nx, a.ny, a.nzl * n, a.nzl),
+                        "bcfortsg, halo exchange)" % (a.nx, a.ny, a.nzl * n, a.nzl, ", strong scaling: total grid fixed" if a.config == "strong" else ""),
             "grid": [a.nx, a.ny, a.nzl * n], "per_gpu": [a.nx, a.ny, a.nzl], "parallelism": "z-slab x%d" % n,
             "l2": "inputs larger than L2 (%.1f GB of fields per GPU)" % (15 * 8 * (a.nx + 4) * (a.ny + 4) * (a.nzl + 4) / 1e9)}
 
@@ -189,6 +297,11 @@ def main_ours(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = S.init(local)
     N = world
+    strong = a.config == "strong"
+    if strong:
+        if a.nz_total % N:
+            raise SystemExit("--config strong: --nz-total must be a multiple of the number of GPUs")
+        a.nzl = a.nz_total // N          # fixed total grid, planes per GPU shrink with N
     nz = a.nzl * N
     prob = CartesianProblem(a.nx, a.ny, nz, h=10.0, vp=4000.0, vs=2000.0, rho=2600.0, gp=30, beta=0.02, corder=1,
                             layers=[(0.6 * nz * 10.0, 6000.0, 3464.0, 2700.0)])
@@ -309,11 +422,13 @@ def main_ours(a):
         # DRAM traffic of that kernel from the committed ncu --set full capture (bytes per point, scaled to this launch)
         traffic, traffic_src, kname = None, None, "k_rhs_fast4<16,EPI_PRED> (fused rhs4sg + predictor + acceleration)"
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01e_traffic.json")))
+            tfile = next(f for f in ("r02_traffic.json", "r01e_traffic.json") if os.path.exists(os.path.join(ROOT, "profiles", f)))
+            tr = json.load(open(os.path.join(ROOT, "profiles", tfile)))
             ent = tr["pred"]
             kname = ent.get("kernel", kname)
             traffic = ent["dram_bytes_per_point"] * a.nx * a.ny * rows / prof["rhs_fast_pred"]["launches_per_step"]
-            traffic_src = "profiles/r01e_traffic.json (ncu dram__bytes_read+write per point of the same kernel, scaled to this launch)"
+            traffic_src = "profiles/%s (ncu --set full dram__bytes_read+write of the same kernel at %s, per point, scaled to this launch)" % (
+                tfile, ent.get("shape", "768x768x96"))
         except Exception:
             pass
         roof = {"bound": "hbm", "kernel": kname,
@@ -321,8 +436,17 @@ def main_ours(a):
                 "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_point": BYTES_PASS_A, "points_per_launch": a.nx * a.ny * rows,
                 "ms_per_launch": dur, "step_frac_of_hbm": BYTES_PER_POINT_STEP * gpts / N / peak}
+        # the co-bound: fp64 pipe.  Measured FMA rate of this GPU (register-only chain kernel) against the kernel's fp64
+        # instruction count per point (ncu: DADD+DMUL+DFMA = 261 warp-instructions per 32 points, profiles/r01d)
+        tf, fr = C.c_double(0), C.c_double(0)
+        if lib.sw4b200_measure_fp64_peak(C.byref(tf), C.byref(fr)) == 0 and fr.value > 0:
+            FP64_INSTR_PER_POINT = 261.0
+            roof["fp64_cobound"] = {"measured_fma_tflops": tf.value, "kernel_fp64_instr_per_point": FP64_INSTR_PER_POINT,
+                                    "pipe_frac": FP64_INSTR_PER_POINT * a.nx * a.ny * rows / prof["rhs_fast_pred"]["launches_per_step"] / (dur * 1e-3) / fr.value,
+                                    "pass_floor_ms": 1e3 * FP64_INSTR_PER_POINT * a.nx * a.ny * rows / prof["rhs_fast_pred"]["launches_per_step"] / fr.value,
+                                    "note": "every fp64 instruction (add, mul or fma) occupies the pipe like an FMA"}
     line = {"metric": "grid-point updates/sec per timestep", "value": gpts, "unit": "Gpts/s", "n_gpus": N, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(a, N),
             "e2e": {"value": gpts_e2e, "unit": "Gpts/s", "h2d_bytes_per_step": int(2 * 3 * 8 * nsel),
                     "d2h_bytes_per_step": int(3 * 8 * nrec), "ms_per_step": ms_e2e / a.steps,
@@ -341,9 +465,115 @@ def main_ours(a):
         dist.destroy_process_group()
 
 
+def main_testil(a):
+    """BASELINE.json config 2: the standalone rhs4sg kernel on the reference harness's analytic 256^3 fields
+    (tests/testil/testil.C:97,209-227,411-420; rate on (n-4)^3 points and 666 flop per point as testil.C:380-390 prints)"""
+    import torch
+    import ctypes as C
+    import sw4lite_b200 as S
+    from tests.fields import Box, harness_fields
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    lib = S.init(0)
+    n = 256
+    box = Box(n, n, n)
+    h = 1.0 / (n - 1)
+    f = harness_fields(box, h)
+    ones = np.ones(n)
+    onesided = (C.c_int * 6)(0, 0, 0, 0, 1, 1)
+    dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    u, mu, la, sx = dev(f["u"]), dev(f["mu"]), dev(f["la"]), dev(ones)
+    lu = torch.zeros(3 * box.npts, dtype=torch.float64, device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr())
+    main = torch.cuda.ExternalStream(lib.sw4b200_stream(0))
+    pts = (n - 4) ** 3
+
+    def apply():
+        S.lib.check(lib.sw4b200_rhs4sg(1, *box.bounds, n - 4, onesided, p(lu), p(u), p(mu), p(la), h, p(sx), p(sx), p(sx), None))
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > the 126 MB L2: written between timed applications
+    for _ in range(a.warmup):
+        apply()
+    sampler = ClockSampler(0); sampler.start()
+    n0 = lib.sw4b200_kernel_launch_count()
+    S.lib.check(lib.sw4b200_profile_reset()); S.lib.check(lib.sw4b200_profile_enable(1))
+    ms = 0.0
+    for _ in range(a.steps):
+        with torch.cuda.stream(main):
+            flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main); apply(); e1.record(main)
+        S.lib.check(lib.sw4b200_sync_device())
+        ms += e0.elapsed_time(e1)
+    S.lib.check(lib.sw4b200_profile_enable(0))
+    launches = lib.sw4b200_kernel_launch_count() - n0
+    clocks = sampler.stop()
+    prof = {}
+    for name in ("rhs_fast_lu", "rhs_fast2_lu", "closure", "rhs_v1"):
+        tot = C.c_double(0); cnt = C.c_longlong(0)
+        lib.sw4b200_profile_read(name.encode(), C.byref(tot), C.byref(cnt))
+        if cnt.value:
+            prof[name] = {"ms_per_step": tot.value / a.steps, "launches_per_step": cnt.value / a.steps}
+    # end to end: host arrays in, host array out (sw4b200_rhs4sg_host stages through its own device buffers)
+    hlu = np.zeros(3 * box.npts)
+    dp = lambda x: x.ctypes.data_as(C.POINTER(C.c_double))
+    hu, hmu, hla = f["u"], f["mu"], f["la"]
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        S.lib.check(lib.sw4b200_rhs4sg_host(1, *box.bounds, n - 4, onesided, dp(hlu), dp(hu), dp(hmu), dp(hla), h, dp(ones), dp(ones), dp(ones)))
+    ms_e2e = 1e3 * (time.perf_counter() - t0)
+    gpts = pts * a.steps / (ms * 1e-3) / 1e9
+    peak, peak_src = peaks()
+    roof = None
+    if "rhs_fast_lu" in prof:
+        dur = prof["rhs_fast_lu"]["ms_per_step"] / prof["rhs_fast_lu"]["launches_per_step"]
+        rows = n - 4 - 12
+        ach = 64.0 * (n - 4) ** 2 * rows / (dur * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "k_rhs_fast4<16,EPI_LU> (interior rows 7..%d)" % (n - 4 - 6), "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_point": 64.0,
+                "points_per_launch": (n - 4) ** 2 * rows, "ms_per_launch": dur, "whole_operator_frac_of_hbm": 64.0 * gpts / peak}
+    line = {"metric": "grid-point updates/sec of one rhs4sg application", "value": gpts, "unit": "Gpts/s", "n_gpus": 1, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "gflops_at_666_flop_per_point": 666.0 * gpts,
+            "config": {"workload": "standalone rhs4sg_rev on the reference kernel harness's analytic fields, %d^3 points (tests/testil), both "
+                                   "SBP closures, corder=1; rate on (n-4)^3 points as testil.C:390" % n, "grid": [n, n, n],
+                       "l2": "L2 flushed (256 MB written) between timed applications"},
+            "e2e": {"value": pts * a.steps / (ms_e2e * 1e-3) / 1e9, "unit": "Gpts/s", "h2d_bytes_per_step": int(8 * 8 * box.npts),
+                    "d2h_bytes_per_step": int(3 * 8 * box.npts), "ms_per_step": ms_e2e / a.steps,
+                    "note": "sw4b200_rhs4sg_host: pageable host arrays in (u, mu, lambda, lu), lu out, synchronous"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": prof}
+    if not a.no_cpu_baseline:
+        try:
+            from oracle import refshim
+            acof, ghcof, bope, _ = refshim.get_stencil_coefficients()
+            try:
+                ncores = len(os.sched_getaffinity(0))
+            except Exception:
+                ncores = os.cpu_count() or 1
+            refshim.set_num_threads(ncores)
+            reps = 3
+            refshim.rhs4sg(1, box.bounds, n - 4, (0, 0, 0, 0, 1, 1), acof, bope, ghcof, hlu, hu, hmu, hla, h, ones, ones, ones)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                refshim.rhs4sg(1, box.bounds, n - 4, (0, 0, 0, 0, 1, 1), acof, bope, ghcof, hlu, hu, hmu, hla, h, ones, ones, ones)
+            dt = (time.perf_counter() - t0) / reps
+            line["cpu_baseline"] = {"value": pts / dt / 1e9, "unit": "Gpts/s", "cores": refshim.num_threads(), "kind": "reference",
+                                    "sample": "rhs4sg_rev of the reference on the same 256^3 fields, mean of %d applications" % reps,
+                                    "gflops_at_666_flop_per_point": 666.0 * pts / dt / 1e9}
+        except Exception as e:
+            line["cpu_baseline"] = {"value": None, "unit": "Gpts/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
+    print(json.dumps(line))
+
+
 if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         main_reference(args)
+    elif args.impl == "reference-cuda":
+        main_reference_cuda(args)
+    elif args.config == "host":
+        main_host(args)
+    elif args.config == "testil256":
+        main_testil(args)
     else:
         main_ours(args)

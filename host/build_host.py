@@ -6,7 +6,7 @@ host/EW_cuda_b200.C + libsw4b200.so.
 
 Recipe = the reference's own CUDA configuration (Makefile.cuda:45-49,99: nvcc -x cu -dc -DSW4_CROUTINES -DSW4_CUDA
 -DSW4_NONBLOCKING, object list minus the three replaced files) for sm_100a.  The two third-party pieces this image
-lacks are stood in for by oracle/stubs/mpi.h (single rank) and oracle/stubs/dspev_stub.C (3x3 symmetric
+lacks are stood in for by host/stubs/mpi.h (single rank) and host/stubs/dspev_stub.C (3x3 symmetric
 eigenvalues), as for the CPU oracle.  Needs /root/reference at BUILD time only; the binary travels to the GPU box.
 """
 import os, subprocess, sys, shutil
@@ -18,7 +18,7 @@ REF = os.environ.get("SW4_REFERENCE", "/root/reference")
 SRC = os.path.join(REF, "src")
 OUT = os.path.join(HERE, "_build")
 OBJ = os.path.join(OUT, "obj")
-STUBS = os.path.join(ROOT, "oracle", "stubs")
+STUBS = os.path.join(HERE, "stubs")
 NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 LIBDIR = os.path.join(ROOT, "sw4lite_b200")
 

@@ -269,6 +269,11 @@ int sw4b200_grid_unpack_halo( sw4b200_grid* g, int side, int with_acc, const dou
 int sw4b200_grid_halo_doubles( sw4b200_grid* g, int with_acc );
 int sw4b200_grid_sync( sw4b200_grid* g );
 
+/* ---------------------------------------------------------------- measurement aid
+ * fp64 FMA throughput of the device (a register-only chain kernel): the co-bound of the stencil kernels next to the HBM
+ * bandwidth ("to be measured"); TFLOP/s at 2 flop per FMA and FMA lane-operations per second. */
+int sw4b200_measure_fp64_peak( double* tflops, double* fma_per_s );
+
 #ifdef __cplusplus
 }
 #endif

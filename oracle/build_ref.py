@@ -5,7 +5,7 @@ they lie under /root/reference/src (never copied), outputs only into oracle/_ref
 Recipe = the reference's own `ckernel=yes` object list (Makefile:229) and flags
 (Makefile:152-164,199: -O3 -fopenmp -DSW4_CROUTINES -DSW4_OPENMP -Isrc -Isrc/double), with
 the two missing third-party pieces replaced by stand-ins written for this repo:
-oracle/stubs/mpi.h (single rank) and oracle/stubs/dspev_stub.C (3x3 symmetric eigenvalues).
+host/stubs/mpi.h (single rank) and host/stubs/dspev_stub.C (3x3 symmetric eigenvalues).
 
 Products:
   oracle/_ref/sw4lite_ref   the unmodified reference program (CPU, OpenMP)
@@ -22,6 +22,7 @@ REF = os.environ.get("SW4_REFERENCE", "/root/reference")
 SRC = os.path.join(REF, "src")
 OUT = os.path.join(HERE, "_ref")
 OBJ = os.path.join(OUT, "obj")
+STUBS = os.path.join(os.path.dirname(HERE), "host", "stubs")   # single-rank mpi.h, 3x3 dspev_ (written for this repository)
 
 OBJS = ("main EW Sarray Source SuperGrid GridPointSource time_functions EW_cuda ew-cfromfort "
         "rhs4sg rhs4sg_rev EWCuda CheckPoint Parallel_IO EW-dg MaterialData MaterialBlock "
@@ -30,7 +31,7 @@ OBJS = ("main EW Sarray Source SuperGrid GridPointSource time_functions EW_cuda 
 
 CXX = os.environ.get("SW4B200_CXX", "/usr/bin/g++")  # $CXX in this image points at a wrapper that cannot link -fopenmp
 FLAGS = ["-O3", "-fopenmp", "-fPIC", "-w", "-DSW4_CROUTINES", "-DSW4_OPENMP",
-         "-I", os.path.join(HERE, "stubs"), "-I", SRC, "-I", os.path.join(SRC, "double")]
+         "-I", STUBS, "-I", SRC, "-I", os.path.join(SRC, "double")]
 TSL_SYMBOL = "_ZN2EW12timesteploopERSt6vectorI6SarraySaIS1_EES4_"
 
 
@@ -58,17 +59,17 @@ def build(verbose=True):
     def cc(name):
         src = os.path.join(SRC, name + ".C")
         obj = os.path.join(OBJ, name + ".o")
-        if not newer(obj, src, os.path.join(HERE, "stubs", "mpi.h")):
+        if not newer(obj, src, os.path.join(STUBS, "mpi.h")):
             run([CXX] + FLAGS + ["-c", src, "-o", obj])
         return obj
 
     with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
         objs = list(ex.map(cc, OBJS))
     stub = os.path.join(OBJ, "dspev_stub.o")
-    if not newer(stub, os.path.join(HERE, "stubs", "dspev_stub.C")):
-        run([CXX, "-O2", "-fPIC", "-c", os.path.join(HERE, "stubs", "dspev_stub.C"), "-o", stub])
+    if not newer(stub, os.path.join(STUBS, "dspev_stub.C")):
+        run([CXX, "-O2", "-fPIC", "-c", os.path.join(STUBS, "dspev_stub.C"), "-o", stub])
     shim = os.path.join(OBJ, "ref_shim.o")
-    if not newer(shim, os.path.join(HERE, "ref_shim.C"), os.path.join(HERE, "stubs", "mpi.h")):
+    if not newer(shim, os.path.join(HERE, "ref_shim.C"), os.path.join(STUBS, "mpi.h")):
         run([CXX] + FLAGS + ["-c", os.path.join(HERE, "ref_shim.C"), "-o", shim])
 
     exe = os.path.join(OUT, "sw4lite_ref")

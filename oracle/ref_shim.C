@@ -509,4 +509,13 @@ int ref_num_threads()
    return n;
 }
 
+// the OpenMP team size of the reference kernels (torchrun exports OMP_NUM_THREADS=1 to its workers: the reference arm of the
+// benchmark sets the host's core count explicitly)
+void ref_set_num_threads( int n )
+{
+#ifdef _OPENMP
+   if( n > 0 ) omp_set_num_threads( n );
+#endif
+}
+
 } // extern "C"

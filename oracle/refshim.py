@@ -66,6 +66,11 @@ def num_threads():
     return lib().ref_num_threads()
 
 
+def set_num_threads(n):
+    """OpenMP team size of the reference kernels (omp_set_num_threads)"""
+    lib().ref_set_num_threads(C.c_int(int(n)))
+
+
 # ---------------------------------------------------------------- kernel level
 def get_stencil_coefficients():
     acof = np.zeros(384); ghcof = np.zeros(6); bope = np.zeros(48); sbop = np.zeros(5)

@@ -208,6 +208,7 @@ int launch_addsgd4_zonly( const Block& b, const Int6& box, double* up, const dou
    const int nx = box.v[1] - box.v[0] + 1, ny = box.v[3] - box.v[2] + 1, nz = box.v[5] - box.v[4] + 1;
    if( beta == 0 || nx <= 0 || ny <= 0 || nz <= 0 ) return 0;
    ProfScope prof( "addsgd", st );
+   ProfScope prof2( "addsgd_zonly", st );
    const long long tiles = (long long)( ( nx + 31 ) / 32 ) * ( ( ny + 7 ) / 8 );
    long long nch = ( 148LL * 32 + tiles - 1 ) / tiles;
    if( nch < 1 ) nch = 1;

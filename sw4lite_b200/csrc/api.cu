@@ -13,6 +13,8 @@
 
 namespace sw4b200 {
 
+int measure_fp64_peak( double* tflops, double* fma_per_s, cudaStream_t st ); // peaks.cu
+
 static thread_local char g_err[1024] = "";
 static int g_launches = 0;
 static cudaStream_t g_streams[4] = { 0, 0, 0, 0 };
@@ -1292,6 +1294,12 @@ int sw4b200_grid_set_stream( sw4b200_grid* g, int st )
    if( st < 0 || st >= 4 ) return set_error( "grid_set_stream: bad stream %d", st );
    g->st = g_streams[st];
    return 0;
+}
+
+int sw4b200_measure_fp64_peak( double* tflops, double* fma_per_s )
+{
+   if( need_init() ) return 1;
+   return measure_fp64_peak( tflops, fma_per_s, g_streams[0] );
 }
 
 int sw4b200_set_option( const char* name, int value )

@@ -1040,6 +1040,7 @@ static int launch_closure_fast_tt( const RhsArgs& a, int side, int kb_lo, int kb
    }
    const Block& b = a.b;
    ProfScope prof( "closure", st );
+   ProfScope prof2( TMA ? "closure_tma" : "closure_cpasync", st ); // (which staging ran: the parity tests assert it)
    dim3 bs( CL_TX, CL_TY, 1 );
    dim3 gs( ( b.nil - 4 + CL_TX - 1 ) / CL_TX, ( b.nj - 4 + CL_TY - 1 ) / CL_TY, 1 );
    k_closure_fast<MODE, TMA><<<gs, bs, smem, st>>>( a, side, kb_lo, kb_hi, maps );

@@ -420,7 +420,7 @@ int launch_fast2_t( const FastArgs& a, cudaStream_t st )
    const Block& b = a.b;
    dim3 bs( C::TX, TY, 1 );
    dim3 gs( ( b.nil - 4 + C::TX - 1 ) / C::TX, ( b.nj - 4 + TY - 1 ) / TY, ( a.khi - a.klo + 1 + a.kchunk - 1 ) / a.kchunk );
-   ProfScope prof( EPI == EPI_PRED ? "rhs_fast_pred" : ( EPI == EPI_CORR ? "rhs_fast_corr" : "rhs_fast_lu" ), st );
+   ProfScope prof( EPI == EPI_PRED ? "rhs_fast2_pred" : ( EPI == EPI_CORR ? "rhs_fast2_corr" : "rhs_fast2_lu" ), st );
    k_rhs_fast2<TY, EPI><<<gs, bs, smem, st>>>( a );
    count_launch();
    return check_launch( "k_rhs_fast2" );

@@ -4,4 +4,5 @@
 #include "rhs4sg_fast4.cu"
 #include "addsgd_fast.cu"
 #include "curvilinear.cu"
+#include "peaks.cu"
 #include "api.cu"

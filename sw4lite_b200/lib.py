@@ -91,6 +91,7 @@ SIGNATURES = {
     "sw4b200_grid_unpack_halo": (I, [VP, I, I, VP, VP]),
     "sw4b200_grid_halo_doubles": (I, [VP, I]),
     "sw4b200_grid_sync": (I, [VP]),
+    "sw4b200_measure_fp64_peak": (I, [c_dp, c_dp]),
 }
 
 _lib = None

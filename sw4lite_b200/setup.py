@@ -1,7 +1,8 @@
 """Problem setup for synthetic runs (bench.py, smoke, examples): what the reference's host code
 (parser + setupRun, EW.C:1865-2146, 4636-4868, 5041-5146; SuperGrid.C:108-198) hands to the time
 loop, restated for Cartesian single-grid problems.  Host-side numpy only; nothing here is on the
-hot path.  Parity of these arrays with the reference is checked in tests/test_setup.py."""
+hot path.  Parity of these arrays (supergrid dc/str/corner, dt, windows) with the reference's own set-up is checked in
+tests/test_setup.py against oracle/_ref."""
 import numpy as np
 
 from .solver import bStressFree, bSuperGrid, bProcessor, boundary_windows
@@ -51,7 +52,7 @@ class CartesianProblem:
     material, point forces with a C6SmoothBump time function."""
 
     def __init__(self, nx, ny, nz, h, vp=4000.0, vs=2000.0, rho=2600.0, gp=30, cfl=1.3, beta=0.02, corder=1,
-                 free_surface=True, layers=None):
+                 free_surface=True, layers=None, free_bottom=False):
         self.nx, self.ny, self.nz, self.h = nx, ny, nz, float(h)
         self.corder = corder
         self.bounds = (-1, nx + 2, -1, ny + 2, -1, nz + 2)
@@ -60,7 +61,9 @@ class CartesianProblem:
         self.bctype = [bSuperGrid] * 6
         if free_surface:
             self.bctype[4] = bStressFree
-        self.onesided = [0, 0, 0, 0, 1 if free_surface else 0, 0]
+        if free_bottom:                 # (a stress-free bottom: the SBP closure of side 5, rhs4sg_rev.C:602-855)
+            self.bctype[5] = bStressFree
+        self.onesided = [0, 0, 0, 0, 1 if free_surface else 0, 1 if free_bottom else 0]
         self.wind = boundary_windows(self.bounds, self.bctype)
         self.beta = beta
         self.gp = gp
@@ -80,7 +83,7 @@ class CartesianProblem:
         ys = (np.arange(-1, ny + 3) - 1) * self.h
         self.dcx, self.strx, self.cox = supergrid_1d(xs, True, True, 0.0, (nx - 1) * self.h, width)
         self.dcy, self.stry, self.coy = supergrid_1d(ys, True, True, 0.0, (ny - 1) * self.h, width)
-        self.dcz, self.strz, self.coz = supergrid_1d(z, not free_surface, True, 0.0, (nz - 1) * self.h, width)
+        self.dcz, self.strz, self.coz = supergrid_1d(z, not free_surface, not free_bottom, 0.0, (nz - 1) * self.h, width)
         # time step (EW::computeDT, EW.C:5041-5066): dt = cfl*h/sqrt(max (4mu+la)/rho)
         self.dt = cfl * self.h / np.sqrt(np.max((4 * muk + lak) / rhk))
         self.sources = []  # (i,j,k, fx,fy,fz, freq, t0)

@@ -44,7 +44,7 @@ class HaloExchange:
         import torch
         self.torch = torch
         self.blk, self.rank, self.nranks = blk, rank, nranks
-        n = 12 * blk.ni * blk.nj          # Up and (after the predictor) the stored acceleration
+        n = 2 * blk.halo_doubles(False)   # Up and (after the predictor) the stored acceleration; device rows may be padded
         kw = dict(dtype=torch.float64, device=device if device is not None else "cpu")
         self.send = [torch.zeros(n, **kw), torch.zeros(n, **kw)]
         self.recv = [torch.zeros(n, **kw), torch.zeros(n, **kw)]

@@ -168,7 +168,7 @@ def test_slabs_on_one_gpu_reproduce_single_block(nslabs):
         k0 = s.bounds[4] - whole.bounds[4]
         s.upload("U", np.ascontiguousarray(full(u0)[:, k0:k0 + s.nk]).ravel())
         s.upload("Um", np.ascontiguousarray(full(um0)[:, k0:k0 + s.nk]).ravel())
-    buf = [[torch.zeros(12 * nij, dtype=torch.float64, device="cuda") for _ in range(2)] for _ in slabs]
+    buf = [[torch.zeros(s.halo_doubles(True), dtype=torch.float64, device="cuda") for _ in range(2)] for s in slabs]
 
     def exchange(with_acc=False):
         for r, s in enumerate(slabs):
