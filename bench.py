@@ -216,7 +216,12 @@ def run_program(exe, grid, steps):
     cols = None
     for n, l in enumerate(lines):
         if l.strip().startswith("Total") and "Scheme" in l and n + 1 < len(lines):
-            cols = [float(x) for x in lines[n + 1].split()]
+            cols = []                   # (the numbers are followed by "Clock tick is ..." on the same line)
+            for tok in lines[n + 1].split():
+                try:
+                    cols.append(float(tok))
+                except ValueError:
+                    break
     solver = [l for l in lines if "Execution time, solver phase" in l]
     if not cols:
         raise RuntimeError("no timing summary in the output of %s: %s" % (exe, r.stdout[-1500:]))
@@ -286,7 +291,7 @@ def main_ours(a):
     import ctypes as C
     import sw4lite_b200 as S
     from sw4lite_b200.setup import CartesianProblem
-    from sw4lite_b200.slabs import HaloExchange, SlabStepper
+    from sw4lite_b200.slabs import SlabStepper
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -312,7 +317,8 @@ def main_ours(a):
         for dj in range(-3, 3):
             for dk in range(-3, 3):
                 prob.add_point_force(ci + di, cj + dj, ck + dk, rng.uniform(-1e12, 1e12, 3), freq=2.0, t0=0.0)
-    blk = prob.make_block(device=local, rank=rank, nranks=N)
+    S.lib.comm_init(rank, N)          # the library's own NCCL communicator for the halo exchange (csrc/exchange.cu)
+    blk = prob.make_block(device=local, rank=rank, nranks=N, comm=True)
     nrec = 0
     if rank == 0:
         ri = np.linspace(40, a.nx - 40, 8).astype(np.int32); rj = np.linspace(40, a.ny - 40, 8).astype(np.int32)
@@ -347,8 +353,7 @@ def main_ours(a):
             dist.barrier()
         S.lib.check(lib.sw4b200_sync_device())
 
-    ex = HaloExchange(blk, rank, N, device="cuda") if N > 1 else None
-    stepper = SlabStepper(blk, ex) if N > 1 else None
+    stepper = SlabStepper(blk, None) if N > 1 else None
 
     def run_steps(first, n, e2e):
         """n steps starting at global step `first`.  e2e: through the per-step public API with host

@@ -268,6 +268,23 @@ int sw4b200_grid_pack_halo( sw4b200_grid* g, int side, int with_acc, double* d_d
 int sw4b200_grid_unpack_halo( sw4b200_grid* g, int side, int with_acc, const double* d_src, void* stream );
 int sw4b200_grid_halo_doubles( sw4b200_grid* g, int with_acc );
 int sw4b200_grid_sync( sw4b200_grid* g );
+/* predictor / corrector phases with the source amplitudes already on the device (3*nsrc doubles, order of
+ * sw4b200_grid_set_source_points; what ForceCU + forcing_dev produce, EW_cuda.C:709, device-routines.C:8306), or NULL */
+int sw4b200_grid_predictor_dev( sw4b200_grid* g, int part, const double* d_f );
+int sw4b200_grid_corrector_dev( sw4b200_grid* g, int part, const double* d_ftt );
+
+/* ---------------------------------------------------------------- halo exchange between z-slabs (one process per GPU)
+ * replaces EW::communicate_array (EW.C:3247-3317) / communicate_arrayCU_X/_Y + pack/unpack_HaloArrayCU_* (EW_cuda.C:1515-1997)
+ * and setup_device_communication_array (:2002): the two face planes of the new solution go straight from the field arrays
+ * into the neighbour's halo planes with grouped ncclSend/ncclRecv on the library's communication stream (no pack kernels,
+ * no staging buffers, no host).  Rendezvous: rank 0 obtains 128 bytes with sw4b200_comm_unique_id and hands them to the
+ * other ranks by any means (a file, torch.distributed, MPI_Bcast); every rank then calls sw4b200_comm_init. */
+int sw4b200_comm_unique_id( void* out128 );
+int sw4b200_comm_init( int rank, int nranks, const void* id128 );
+int sw4b200_comm_finalize( void );
+int sw4b200_grid_set_neighbours( sw4b200_grid* g, int rank_lo, int rank_hi );   /* -1: no neighbour on that face */
+int sw4b200_grid_exchange_begin( sw4b200_grid* g, int with_acc );              /* after the face rows (part 1)   */
+int sw4b200_grid_exchange_end( sw4b200_grid* g );                              /* before the boundary conditions  */
 
 /* ---------------------------------------------------------------- measurement aid
  * fp64 FMA throughput of the device (a register-only chain kernel): the co-bound of the stencil kernels next to the HBM

@@ -11,7 +11,8 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sw4lite_b200.setup import CartesianProblem
-from sw4lite_b200.slabs import HaloExchange, SlabStepper
+from sw4lite_b200.slabs import SlabStepper
+from sw4lite_b200 import lib as L
 
 
 def main():
@@ -27,11 +28,12 @@ def main():
     u0 = r.uniform(-1e-3, 1e-3, 3 * prob.npts); um0 = u0 + r.uniform(-1e-5, 1e-5, 3 * prob.npts)
     nij = prob.ni * prob.nj
     full = lambda a: a.reshape(3, prob.nk, nij)
-    blk = prob.make_block(device=local, rank=rank, nranks=world)
+    L.init(local); L.comm_init(rank, world)
+    blk = prob.make_block(device=local, rank=rank, nranks=world, comm=True)
     k0 = blk.bounds[4] - prob.bounds[4]
     blk.upload("U", np.ascontiguousarray(full(u0)[:, k0:k0 + blk.nk]).ravel())
     blk.upload("Um", np.ascontiguousarray(full(um0)[:, k0:k0 + blk.nk]).ravel())
-    stepper = SlabStepper(blk, HaloExchange(blk, rank, world, device="cuda"))
+    stepper = SlabStepper(blk, None)
     nsteps = 6
     t = 0.0
     for s in range(nsteps):

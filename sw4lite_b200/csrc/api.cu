@@ -14,6 +14,15 @@
 namespace sw4b200 {
 
 int measure_fp64_peak( double* tflops, double* fma_per_s, cudaStream_t st ); // peaks.cu
+// exchange.cu
+int comm_unique_id( void* out128 );
+int comm_init( int rank, int nranks, const void* id128 );
+int comm_finalize();
+int comm_rank();
+int comm_size();
+int exchange_field( const Block& b, double* field, int peer_lo, int peer_hi, cudaStream_t st );
+int exchange_group_start();
+int exchange_group_end();
 
 static thread_local char g_err[1024] = "";
 static int g_launches = 0;
@@ -269,6 +278,9 @@ struct sw4b200_grid
    int nrec;
    long long* d_recidx;
    double *d_rec, *h_rec;
+   // z-slab neighbours (ranks of the communicator, -1: none) and the events that order the exchange against the compute stream
+   int peer_lo, peer_hi;
+   cudaEvent_t ev_face, ev_halo;
 };
 
 extern "C" {
@@ -766,6 +778,7 @@ sw4b200_grid* sw4b200_grid_create( const sw4b200_grid_desc* desc )
    g->b = make_block( desc->corder, desc->ifirst, desc->ilast, desc->jfirst, desc->jlast, desc->kfirst, desc->klast, use_fast_path() );
    g->st = g_streams[0];
    g->fast = desc->corder == 1 && !desc->curvilinear && use_fast_path();
+   g->peer_lo = g->peer_hi = -1;
    if( grid_alloc( g ) )
    {
       const std::string msg = g_err; // (grid_destroy does not overwrite it, but keep the first cause)
@@ -792,6 +805,8 @@ int sw4b200_grid_destroy( sw4b200_grid* g )
    if( g->d_recidx ) cudaFree( g->d_recidx );
    if( g->h_f ) cudaFreeHost( g->h_f );
    if( g->h_rec ) cudaFreeHost( g->h_rec );
+   if( g->ev_face ) cudaEventDestroy( g->ev_face );
+   if( g->ev_halo ) cudaEventDestroy( g->ev_halo );
    delete g;
    return 0;
 }
@@ -1212,6 +1227,61 @@ int sw4b200_grid_corrector_part( sw4b200_grid* g, int part, const double* h_ftt 
    if( part != 2 && upload_forces( g, h_ftt, 1, &d_ftt ) ) return 1;
    if( h_ftt == 0 ) d_ftt = 0;
    return corrector_part( g, part, d_ftt );
+}
+
+// the same phases with the source amplitudes already on the device (3*nsrc doubles in the order of
+// sw4b200_grid_set_source_points, e.g. evaluated there by the caller's own time-function kernel), or NULL
+int sw4b200_grid_predictor_dev( sw4b200_grid* g, int part, const double* d_f )
+{
+   if( part < 0 || part > 2 ) return set_error( "predictor_dev: part must be 0, 1 or 2" );
+   return predictor_part( g, part, g->nsrc ? d_f : 0 );
+}
+int sw4b200_grid_corrector_dev( sw4b200_grid* g, int part, const double* d_ftt )
+{
+   if( part < 0 || part > 2 ) return set_error( "corrector_dev: part must be 0, 1 or 2" );
+   return corrector_part( g, part, g->nsrc ? d_ftt : 0 );
+}
+
+// ---- halo exchange between z-slabs inside the library (exchange.cu)
+int sw4b200_comm_unique_id( void* out128 ) { return comm_unique_id( out128 ); }
+int sw4b200_comm_init( int rank, int nranks, const void* id128 )
+{
+   if( need_init() ) return 1;
+   return comm_init( rank, nranks, id128 );
+}
+int sw4b200_comm_finalize( void ) { return comm_finalize(); }
+int sw4b200_grid_set_neighbours( sw4b200_grid* g, int rank_lo, int rank_hi )
+{
+   if( ( rank_lo >= 0 ) != ( g->d.halo_lo != 0 ) || ( rank_hi >= 0 ) != ( g->d.halo_hi != 0 ) )
+      return set_error( "grid_set_neighbours: neighbours (%d,%d) do not match the halo faces of the block (%d,%d)", rank_lo, rank_hi,
+			g->d.halo_lo, g->d.halo_hi );
+   if( rank_lo >= comm_size() || rank_hi >= comm_size() ) return set_error( "grid_set_neighbours: rank out of range" );
+   g->peer_lo = rank_lo; g->peer_hi = rank_hi;
+   if( !g->ev_face ) CUDA_OK( cudaEventCreateWithFlags( &g->ev_face, cudaEventDisableTiming ) );
+   if( !g->ev_halo ) CUDA_OK( cudaEventCreateWithFlags( &g->ev_halo, cudaEventDisableTiming ) );
+   return 0;
+}
+// start moving the face planes of Up (with_acc: and of the stored acceleration, after the predictor) to / from the
+// neighbours on the communication stream, once everything queued on the block's stream so far (the face rows) is done
+int sw4b200_grid_exchange_begin( sw4b200_grid* g, int with_acc )
+{
+   if( g->peer_lo < 0 && g->peer_hi < 0 ) return 0;
+   cudaStream_t cs = g_streams[3];
+   CUDA_OK( cudaEventRecord( g->ev_face, g->st ) );
+   CUDA_OK( cudaStreamWaitEvent( cs, g->ev_face, 0 ) );
+   if( exchange_group_start() ) return 1;
+   int rc = exchange_field( g->b, g->Up, g->peer_lo, g->peer_hi, cs );
+   if( !rc && with_acc && g->fast ) rc = exchange_field( g->b, g->Uacc, g->peer_lo, g->peer_hi, cs );
+   if( exchange_group_end() || rc ) return 1;
+   CUDA_OK( cudaEventRecord( g->ev_halo, cs ) );
+   return 0;
+}
+// everything queued on the block's stream after this call sees the received halo planes
+int sw4b200_grid_exchange_end( sw4b200_grid* g )
+{
+   if( g->peer_lo < 0 && g->peer_hi < 0 ) return 0;
+   CUDA_OK( cudaStreamWaitEvent( g->st, g->ev_halo, 0 ) );
+   return 0;
 }
 
 // ---- device-resident runs: source amplitudes of all steps uploaded once, receivers kept on the device

@@ -5,4 +5,5 @@
 #include "addsgd_fast.cu"
 #include "curvilinear.cu"
 #include "peaks.cu"
+#include "exchange.cu"
 #include "api.cu"

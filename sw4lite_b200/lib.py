@@ -91,6 +91,14 @@ SIGNATURES = {
     "sw4b200_grid_unpack_halo": (I, [VP, I, I, VP, VP]),
     "sw4b200_grid_halo_doubles": (I, [VP, I]),
     "sw4b200_grid_sync": (I, [VP]),
+    "sw4b200_grid_predictor_dev": (I, [VP, I, VP]),
+    "sw4b200_grid_corrector_dev": (I, [VP, I, VP]),
+    "sw4b200_comm_unique_id": (I, [VP]),
+    "sw4b200_comm_init": (I, [I, I, VP]),
+    "sw4b200_comm_finalize": (I, []),
+    "sw4b200_grid_set_neighbours": (I, [VP, I, I]),
+    "sw4b200_grid_exchange_begin": (I, [VP, I]),
+    "sw4b200_grid_exchange_end": (I, [VP]),
     "sw4b200_measure_fp64_peak": (I, [c_dp, c_dp]),
 }
 
@@ -131,3 +139,25 @@ def init(device=0):
     check(lib.sw4b200_init(device))
     _inited[device] = True
     return lib
+
+
+def comm_init(rank, nranks):
+    """communicator of the library's halo exchange (csrc/exchange.cu): rank 0 creates the NCCL unique id, torch.distributed
+    (already initialised by the caller; plumbing only) hands it to the other ranks"""
+    import torch
+    import torch.distributed as dist
+    lib = load()
+    buf = (C.c_ubyte * 128)()
+    if nranks > 1:
+        if rank == 0:
+            check(lib.sw4b200_comm_unique_id(buf))
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, 0)
+        for n, v in enumerate(t.cpu().tolist()):
+            buf[n] = v
+    check(lib.sw4b200_comm_init(int(rank), int(nranks), buf))
+
+
+def comm_finalize():
+    check(load().sw4b200_comm_finalize())

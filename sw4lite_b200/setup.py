@@ -128,7 +128,8 @@ class CartesianProblem:
             onesided[5] = 0; bctype[5] = bProcessor
         return tuple(bounds), onesided, bctype, halo_lo, halo_hi
 
-    def make_block(self, device=0, rank=0, nranks=1):
+    def make_block(self, device=0, rank=0, nranks=1, comm=False):
+        """comm: the library's communicator spans the `nranks` slabs (lib.comm_init): register the z-neighbours"""
         from .solver import GridBlock
         bounds, onesided, bctype, halo_lo, halo_hi = self.slab(rank, nranks)
         g = GridBlock(self.corder, bounds, (self.nx, self.ny, self.nz), self.h, self.dt, onesided,
@@ -141,6 +142,8 @@ class CartesianProblem:
         for name in ("strz", "dcz", "coz"):
             g.upload(name, getattr(self, name)[ks])
         g.fill_profile("mu", self.muk[ks]); g.fill_profile("lambda", self.lak[ks]); g.fill_profile("rho", self.rhk[ks])
+        if comm and nranks > 1:
+            g.set_neighbours(rank - 1 if halo_lo else None, rank + 1 if halo_hi else None)
         g.src_sel = [n for n, s in enumerate(self.sources) if bounds[4] + 2 <= s[2] <= bounds[5] - 2]
         if g.src_sel:
             g.set_source_points(self.source_points()[g.src_sel])

@@ -3,16 +3,13 @@ replaces the reference's MPI x-y halo swap (EW::communicate_array, EW.C:3247-331
 communicate_arrayCU_X/Y, EW_cuda.C:1699-1997) on this path: one process per GPU, 2 planes of the new
 solution per face, moved after the predictor and after the corrector (EW.C:2616, 2743).
 
-With the (i,j,k,c) layout a k-plane of one component is one contiguous run of ni*nj doubles, so a halo
-is 3 contiguous runs per face.  Two transports:
-  * "nccl": torch.distributed batched isend/irecv on packed halo buffers (also what the CPU `gloo`
-    tests drive through a numpy stand-in for the block),
-  * "p2p":  CUDA IPC peer mappings -- every rank copies its face planes straight into the neighbour's
-    halo planes over NVLink (cudaMemcpyAsync on peer pointers, no staging, no NCCL on the data path),
-    ordered by CUDA IPC events.
-The exchange of the face planes overlaps the computation of the slab's remaining rows: the face rows
-are computed first (sw4b200_grid_*_part(1)), their transfer is launched on a second stream, then the
-bulk (part 2) runs; the boundary conditions wait for both.
+With the (i,j,k,c) layout a k-plane of one component is one contiguous run of ni*nj doubles, so a halo is 3 contiguous
+runs per face and needs no pack kernel: on the GPU the exchange lives in the library (csrc/exchange.cu, sw4b200_grid_exchange_begin /
+_end: grouped ncclSend / ncclRecv straight from the field arrays into the neighbour's halo planes, NCCL over NVLink).  The
+exchange of the face planes overlaps the computation of the slab's remaining rows: the face rows are computed first
+(sw4b200_grid_*_part(1)), their transfer is started on the communication stream, then the bulk (part 2) runs; the boundary
+conditions wait for both.  `HaloExchange` below is the host-logic stand-in used by the CPU (gloo) tests, where a numpy block
+takes the place of the device block.
 """
 import numpy as np
 
@@ -37,7 +34,8 @@ def slab_range(nz, rank, nranks):
 
 
 class HaloExchange:
-    """moves the face planes of Up between neighbouring slabs.  `blk` needs: ni, nj, pack(side) ->
+    """CPU stand-in of the library's exchange (tests/test_slabs_cpu.py): moves the face planes of Up between neighbouring slabs
+    with torch.distributed send/recv on packed buffers.  `blk` needs: ni, nj, pack(side) ->
     tensor(3*2*ni*nj), unpack(side, tensor); torch.distributed must be initialised when nranks > 1."""
 
     def __init__(self, blk, rank, nranks, device=None):

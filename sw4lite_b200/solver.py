@@ -164,49 +164,18 @@ class GridBlock:
     def halo_doubles(self, with_acc):
         return int(self.lib.sw4b200_grid_halo_doubles(self.h, int(with_acc)))
 
-    def _streams(self):
-        import torch
-        if not hasattr(self, "_main"):
-            self._main = torch.cuda.ExternalStream(self.lib.sw4b200_stream(0))
-            self._comm = torch.cuda.ExternalStream(self.lib.sw4b200_stream(1))
-            self._ev_face = torch.cuda.Event()
-            self._ev_halo = torch.cuda.Event()
-        return self._main, self._comm
+    # ---- halo exchange inside the library (csrc/exchange.cu): grouped ncclSend/ncclRecv straight from / into the field
+    # arrays on the library's communication stream.  `ex` is unused here (the CPU stand-in of the gloo tests needs it).
+    def set_neighbours(self, rank_lo, rank_hi):
+        L.check(self.lib.sw4b200_grid_set_neighbours(self.h, -1 if rank_lo is None else int(rank_lo), -1 if rank_hi is None else int(rank_hi)))
 
-    def begin_exchange(self, ex, with_acc=False):
-        """start moving the face planes of Up on the communication stream; the caller goes on
-        launching the bulk rows on the compute stream"""
-        import torch
-        import torch.distributed as dist
-        main, comm = self._streams()
-        self._ev_face.record(main)
-        comm.wait_event(self._ev_face)
-        cs = C.c_void_p(comm.cuda_stream)
-        n = self.halo_doubles(with_acc)
-        self._works = []
-        with torch.cuda.stream(comm):
-            ops = []
-            for side, peer in ((0, ex.lo), (1, ex.hi)):
-                if peer is None:
-                    continue
-                self.pack(side, ex.send[side], cs, with_acc)
-                ops.append(dist.P2POp(dist.isend, ex.send[side][:n], peer))
-                ops.append(dist.P2POp(dist.irecv, ex.recv[side][:n], peer))
-            if ops:
-                self._works = dist.batch_isend_irecv(ops)
+    def begin_exchange(self, ex=None, with_acc=False):
+        """start moving the face planes of Up (and of the stored acceleration) once the face rows queued so far are done;
+        the caller goes on launching the bulk rows on the compute stream"""
+        L.check(self.lib.sw4b200_grid_exchange_begin(self.h, int(with_acc)))
 
-    def end_exchange(self, ex, with_acc=False):
-        import torch
-        main, comm = self._streams()
-        cs = C.c_void_p(comm.cuda_stream)
-        with torch.cuda.stream(comm):
-            for w in self._works:
-                w.wait()
-            for side, peer in ((0, ex.lo), (1, ex.hi)):
-                if peer is not None:
-                    self.unpack(side, ex.recv[side], cs, with_acc)
-        self._ev_halo.record(comm)
-        main.wait_event(self._ev_halo)
+    def end_exchange(self, ex=None, with_acc=False):
+        L.check(self.lib.sw4b200_grid_exchange_end(self.h))
 
     def record(self):
         out = np.zeros(3 * max(self.nrec, 1))

@@ -108,7 +108,8 @@ def test_bench_kernels_step_matches_oracle(shape):
     assert n["rhs_fast_pred"] >= 4 and n["rhs_fast_corr"] >= 4, n
     assert n["rhs_fast2_pred"] == 0 and n["rhs_fast2_corr"] == 0 and n["rhs_v1"] == 0, n
     assert n["closure_tma"] == 8 and n["closure_cpasync"] == 0, n
-    assert n["addsgd_zonly"] >= 4, n
+    if min(shape[0], shape[1]) > 2 * 8 + 6:      # (room between the x / y supergrid layers: z-only damping boxes exist)
+        assert n["addsgd_zonly"] >= 4, n
     pitch = lib.sw4b200_grid_row_pitch(blk.h)
     assert pitch % 2 == 0 and pitch - (shape[0] + 4) == (shape[0] + 4) % 2
     print("shape %s pitch %d: worst per-step rel. diff %.3g, launches %s" % (shape, pitch, worst, n))
