@@ -9,6 +9,12 @@
 // with -DSW4_CUDA, leaves out EW_cuda.C / device-routines.C / EWCuda.C, and links this file and libsw4b200.so
 // instead: `sw4lite_b200 file.in` is then the reference program running on the B200 kernels of this repository.
 //
+// The device-resident state of every grid lives in a sw4b200_grid object (the grid-block level of the C-ABI): rows padded
+// to an even pitch (so the reference's odd-ni grids run on the TMA-staged kernels), stored acceleration, sparse forcing,
+// box-decomposed supergrid damping.  One time step is two fused passes per grid (sw4b200_grid_predictor_dev /
+// _corrector_dev) plus the boundary conditions; the reference's Sarray device copies are only written when the host is
+// about to read them (checkpoints, the final error norm).
+//
 // There is no CPU fallback here: when libsw4b200 cannot initialise a device the program stops.
 #include "mpi.h"
 #include "sw4.h"
@@ -18,7 +24,9 @@
 #include "GridPointSource.h"
 #include "TimeSeries.h"
 #include "Source.h"
+#include "CheckPoint.h"
 #include "../include/sw4b200.h"
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -45,16 +53,35 @@ void* stream0() { return sw4b200_stream( 0 ); }
 struct GridSources
 {
    int n;
-   vector<int> first, last; // ranges into m_point_sources
-   long long* d_idx;
+   vector<int> ijk; // the unique source points of the grid
+   long long* d_idx; // flat indices in the reference's (unpadded) layout, for the operator-level calls
    double *d_f, *h_f;
 };
 vector<GridSources> g_src;
 bool g_src_built = false;
 
-// device pointers of the solution arrays of the current step (for the receivers)
-vector<double*> g_up, g_um;
-vector<double*> g_lu; // scratch L(u) of the curvilinear grid
+vector<double*> g_lu; // scratch L(u) of the curvilinear grid (unfused operator calls only)
+
+// one device-resident grid block per grid; the time loop's phases run on them
+vector<sw4b200_grid*> g_grid;
+bool g_imported = false;  // the initial U, Um have been moved into the grid blocks
+bool g_corr_done = false; // the corrector of the current step has run (the next enforceBCCU finishes the step)
+double g_t_step = 0;	  // time at the start of the current step (ForceCU)
+vector<Sarray*> g_sUp, g_sU; // the reference's arrays holding Up / U of the current step (export targets)
+
+// read-only view of CheckPoint::timeToWrite (CheckPoint.C:205-230), which itself advances the check point's state
+struct CheckPointPeek : public CheckPoint
+{
+   static bool due( const CheckPoint* c, float_sw4 time, int cycle, float_sw4 dt )
+   {
+      const CheckPointPeek* p = static_cast<const CheckPointPeek*>( c );
+      bool do_it = cycle == p->mWritingCycle;
+      if( p->mCycleInterval != 0 && cycle % p->mCycleInterval == 0 && time >= p->mStartTime ) do_it = true;
+      if( p->mTime > 0.0 && p->mTime <= time + dt * 0.5 && !p->m_time_done ) do_it = true;
+      if( p->mTimeInterval != 0.0 && p->mNextTime <= time + dt * 0.5 && time >= p->mStartTime ) do_it = true;
+      return do_it;
+   }
+};
 
 double** g_bforce_host_ptrs( vector<double**>& dev_BCForcing, int g ) { return dev_BCForcing[g]; }
 
@@ -141,20 +168,9 @@ void EW::copy_supergrid_arrays_to_device()
    }
 }
 
-void EW::copy_material_to_device()
-{
-   for( int g = 0; g < mNumberOfGrids; g++ )
-   {
-      mMu[g].copy_to_device( m_cuobj );
-      mLambda[g].copy_to_device( m_cuobj );
-      mRho[g].copy_to_device( m_cuobj );
-   }
-   if( topographyExists() )
-   {
-      mJ.copy_to_device( m_cuobj );
-      mMetric.copy_to_device( m_cuobj );
-   }
-}
+// materials, metric and the supergrid arrays are uploaded into the grid blocks by setup_device_communication_array (the last
+// set-up call before the time loop, EW.C:2524); the reference's own device copies are not needed
+void EW::copy_material_to_device() {}
 
 void EW::copy_bcforcing_arrays_to_device()
 {
@@ -181,8 +197,49 @@ void EW::copy_bcforcing_arrays_to_device()
 // boundary types and windows are passed by value to sw4b200_bcfortsg: nothing to copy
 void EW::copy_bctype_arrays_to_device() {}
 void EW::copy_bndrywindow_arrays_to_device() {}
-// single rank per GPU in this build: the x-y halo swap of the reference has no neighbour
-void EW::setup_device_communication_array() {}
+static void build_sources( EW* ew );
+
+// Called right before the time loop (EW.C:2524), when dt, the boundary windows, the supergrid arrays and the sources are
+// final: build the device-resident grid blocks.  (The x-y halo swap the reference sets up here has no neighbour: one rank per
+// GPU in this build; multi-GPU runs decompose in z through sw4b200_grid_exchange_*, host/slab_driver.C.)
+void EW::setup_device_communication_array()
+{
+   if( m_ndevice <= 0 ) return;
+   build_sources( this );
+   g_grid.assign( mNumberOfGrids, (sw4b200_grid*)0 );
+   for( int g = 0; g < mNumberOfGrids; g++ )
+   {
+      sw4b200_grid_desc d;
+      memset( &d, 0, sizeof( d ) );
+      d.corder = Sarray::m_corder ? 1 : 0;
+      d.ifirst = m_iStart[g]; d.ilast = m_iEnd[g]; d.jfirst = m_jStart[g]; d.jlast = m_jEnd[g]; d.kfirst = m_kStart[g]; d.klast = m_kEnd[g];
+      d.nx = m_global_nx[g]; d.ny = m_global_ny[g]; d.nz = m_global_nz[g];
+      d.h = mGridSize[g]; d.dt = mDt;
+      for( int s = 0; s < 6; s++ ) { d.onesided[s] = m_onesided[g][s]; d.bctype[s] = (int)m_bcType[g][s]; }
+      for( int s = 0; s < 36; s++ ) d.wind[s] = m_BndryWindow[g][s];
+      d.sg_order = m_use_supergrid ? m_sg_damping_order : 0;
+      d.beta = m_use_supergrid ? m_supergrid_damping_coefficient : 0.0;
+      d.curvilinear = topographyExists() && g == mNumberOfGrids - 1;
+      sw4b200_grid* G = sw4b200_grid_create( &d );
+      if( !G ) ok( 1, "sw4b200_grid_create" );
+      g_grid[g] = G;
+      B200( sw4b200_grid_upload( G, "mu", mMu[g].c_ptr() ) );
+      B200( sw4b200_grid_upload( G, "lambda", mLambda[g].c_ptr() ) );
+      B200( sw4b200_grid_upload( G, "rho", mRho[g].c_ptr() ) );
+      if( d.curvilinear )
+      {
+	 B200( sw4b200_grid_upload( G, "jac", mJ.c_ptr() ) );
+	 B200( sw4b200_grid_upload( G, "metric", mMetric.c_ptr() ) );
+      }
+      B200( sw4b200_grid_upload( G, "strx", m_sg_str_x[g] ) ); B200( sw4b200_grid_upload( G, "stry", m_sg_str_y[g] ) );
+      B200( sw4b200_grid_upload( G, "strz", m_sg_str_z[g] ) );
+      B200( sw4b200_grid_upload( G, "dcx", m_sg_dc_x[g] ) ); B200( sw4b200_grid_upload( G, "dcy", m_sg_dc_y[g] ) );
+      B200( sw4b200_grid_upload( G, "dcz", m_sg_dc_z[g] ) );
+      B200( sw4b200_grid_upload( G, "cox", m_sg_corner_x[g] ) ); B200( sw4b200_grid_upload( G, "coy", m_sg_corner_y[g] ) );
+      B200( sw4b200_grid_upload( G, "coz", m_sg_corner_z[g] ) );
+      if( g_src[g].n > 0 ) B200( sw4b200_grid_set_source_points( G, g_src[g].n, g_src[g].ijk.data() ) );
+   }
+}
 void EW::pack_HaloArrayCU( Sarray&, int, int ) {}
 void EW::unpack_HaloArrayCU( Sarray&, int, int ) {}
 void EW::communicate_arrayCU( Sarray&, int, int ) {}
@@ -195,22 +252,25 @@ void EW::communicate_arrayCU_Y( Sarray&, int, int ) {}
 
 bool EW::check_for_nan_GPU( vector<Sarray>& a_U, int verbose, string name )
 {
+   (void)a_U; (void)verbose;
+   // the state lives in the grid blocks: whatever array the loop asks about, the three time levels are checked
    bool clean = true;
-   for( int g = 0; g < mNumberOfGrids; g++ )
-   {
-      const size_t n = (size_t)a_U[g].m_nc * a_U[g].m_ni * a_U[g].m_nj * a_U[g].m_nk;
-      vector<double> h( n );
-      B200( sw4b200_memcpy_d2h( h.data(), a_U[g].dev_ptr(), n * sizeof( double ), 0 ) );
-      B200( sw4b200_sync_stream( 0 ) );
-      size_t cnt = 0, first = 0;
-      for( size_t q = 0; q < n; q++ )
-	 if( h[q] != h[q] ) { if( cnt == 0 ) first = q; cnt++; }
-      if( cnt )
+   const char* fields[3] = { "Um", "U", "Up" };
+   for( int g = 0; g < mNumberOfGrids && !g_grid.empty(); g++ )
+      for( int f = 0; f < 3; f++ )
       {
-	 cout << "grid " << g << " array " << name << " found " << cnt << " nans. First nan at linear index " << first << endl;
-	 clean = false;
+	 vector<double> h( sw4b200_grid_array_size( g_grid[g], fields[f] ) );
+	 B200( sw4b200_grid_download( g_grid[g], fields[f], h.data() ) );
+	 size_t cnt = 0, first = 0;
+	 for( size_t q = 0; q < h.size(); q++ )
+	    if( h[q] != h[q] ) { if( cnt == 0 ) first = q; cnt++; }
+	 if( cnt )
+	 {
+	    cout << "grid " << g << " array " << fields[f] << " (asked for " << name << ") found " << cnt << " nans. First nan at linear index "
+		 << first << endl;
+	    clean = false;
+	 }
       }
-   }
    return clean;
 }
 
@@ -258,6 +318,7 @@ static int g_nunique = 0;
 
 static void build_sources( EW* ew )
 {
+   if( g_src_built ) return;
    g_src.assign( ew->mNumberOfGrids, GridSources() );
    for( int g = 0; g < ew->mNumberOfGrids; g++ ) { g_src[g].n = 0; g_src[g].d_idx = 0; g_src[g].d_f = 0; g_src[g].h_f = 0; }
    vector<vector<long long> > idx( ew->mNumberOfGrids );
@@ -272,6 +333,7 @@ static void build_sources( EW* ew )
       const long long ni = ew->m_iEnd[g] - ew->m_iStart[g] + 1, nj = ew->m_jEnd[g] - ew->m_jStart[g] + 1;
       idx[g].push_back( ( p->m_i0 - ew->m_iStart[g] ) + ni * ( p->m_j0 - ew->m_jStart[g] ) + ni * nj * ( p->m_k0 - ew->m_kStart[g] ) );
       uniq[g].push_back( r );
+      g_src[g].ijk.push_back( p->m_i0 ); g_src[g].ijk.push_back( p->m_j0 ); g_src[g].ijk.push_back( p->m_k0 );
    }
    if( nu > 0 )
    {
@@ -303,6 +365,7 @@ static void build_sources( EW* ew )
 void EW::ForceCU( float_sw4 t, Sarray* dev_F, bool tt, int st )
 {
    (void)dev_F; (void)st;
+   if( !tt ) g_t_step = t;
    if( !g_src_built ) build_sources( this );
    if( g_nunique == 0 ) return;
    b200_eval_forces<<<( g_nunique + 127 ) / 128, 128, 0, (cudaStream_t)stream0()>>>( t, dev_point_sources, dev_identsources, g_nunique,
@@ -337,74 +400,77 @@ static double* lu_scratch( EW* ew, int g )
 // --------------------------------------------------------------------------------------------- time step
 #define BOUNDS( g ) m_iStart[g], m_iEnd[g], m_jStart[g], m_jEnd[g], m_kStart[g], m_kEnd[g]
 
-// fused rhs4sg + predictor (+ sparse forcing): replaces RHSPredCU_boundary + RHSPredCU_center (EW_cuda.C:1228-1320)
+// ---- grid-block time step.  EW::timesteploop (EW.C:2527-2842) calls, in this order: ForceCU(t), RHSPredCU_boundary,
+// RHSPredCU_center, halo members, cartesian_bc_forcingCU + enforceBCCU, ForceCU(t, tt), evalDpDmInTimeCU, RHSCorrCU_boundary,
+// addSuperGridDampingCU_upper_boundary, RHSCorrCU_center, addSuperGridDampingCU_center, halo members, cartesian_bc_forcingCU +
+// enforceBCCU, sync_stream, (check points), extractRecordDataCU, cycleSolutionArrays.  Here a step is
+//   RHSPredCU_center  -> sw4b200_grid_predictor_dev  (fused rhs4sg + predictor + stored acceleration + sparse forcing)
+//   enforceBCCU       -> sw4b200_grid_enforce_bc (+ enforce_cart_topo)
+//   RHSCorrCU_center  -> sw4b200_grid_corrector_dev  (fused rhs4sg + corrector on the stored acceleration + F_tt + damping)
+//   enforceBCCU       -> boundary conditions; the reference's device arrays are refreshed only if the host will read them
+// and the other members have nothing left to do.  cycleSolutionArrays is the reference's own: the grid blocks rotate at the
+// start of the next step instead.
+static void import_initial_data( EW* ew, vector<Sarray>& a_U, vector<Sarray>& a_Um )
+{
+   // U, Um as the host holds them at the start of the loop (zero, or a restart file's: EW.C:2403-2415)
+   for( int g = 0; g < ew->mNumberOfGrids; g++ )
+   {
+      B200( sw4b200_grid_upload( g_grid[g], "U", a_U[g].c_ptr() ) );
+      B200( sw4b200_grid_upload( g_grid[g], "Um", a_Um[g].c_ptr() ) );
+   }
+   g_imported = true;
+}
+
+// grid block -> the reference's (unpadded) device array, so that Sarray::copy_from_device sees the current values
+static void export_field( int g, const char* name, Sarray& dst )
+{
+   const double* src = (const double*)sw4b200_grid_device_ptr( g_grid[g], name );
+   const size_t pitch = (size_t)sw4b200_grid_row_pitch( g_grid[g] ), ni = dst.m_ni;
+   const size_t rows = (size_t)dst.m_nc * dst.m_nj * dst.m_nk;
+   cudaError_t e;
+   if( Sarray::m_corder && pitch != ni )
+      e = cudaMemcpy2DAsync( dst.dev_ptr(), ni * 8, src, pitch * 8, ni * 8, rows, cudaMemcpyDeviceToDevice, (cudaStream_t)stream0() );
+   else
+      e = cudaMemcpyAsync( dst.dev_ptr(), src, rows * ni * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream0() );
+   if( e != cudaSuccess ) { fprintf( stderr, "sw4lite_b200: export of %s failed: %s\n", name, cudaGetErrorString( e ) ); exit( 1 ); }
+}
+
 void EW::RHSPredCU_boundary( vector<Sarray>&, vector<Sarray>&, vector<Sarray>&, vector<Sarray>&, vector<Sarray>&,
 			     vector<Sarray>&, vector<Sarray>&, int ) {}
 void EW::RHSPredCU_center( vector<Sarray>& a_Up, vector<Sarray>& a_U, vector<Sarray>& a_Um, vector<Sarray>& a_Mu,
 			   vector<Sarray>& a_Lambda, vector<Sarray>& a_Rho, vector<Sarray>& a_F, int st )
 {
-   (void)a_F; (void)st;
-   g_up.resize( mNumberOfGrids ); g_um.resize( mNumberOfGrids );
-   const double dt2 = mDt * mDt;
+   (void)a_Mu; (void)a_Lambda; (void)a_Rho; (void)a_F; (void)st;
+   if( !g_imported ) import_initial_data( this, a_U, a_Um );
+   else
+      for( int g = 0; g < mNumberOfGrids; g++ ) B200( sw4b200_grid_cycle( g_grid[g] ) ); // the rotation of the previous step
+   g_sUp.resize( mNumberOfGrids ); g_sU.resize( mNumberOfGrids );
    for( int g = 0; g < mNumberOfGrids; g++ )
    {
-      g_up[g] = a_Up[g].dev_ptr(); g_um[g] = a_Um[g].dev_ptr();
-      if( g < mNumberOfCartesianGrids )
-	 B200( sw4b200_rhs4_pred( Sarray::m_corder, BOUNDS( g ), m_global_nz[g], m_onesided[g], a_Up[g].dev_ptr(), a_U[g].dev_ptr(),
-				  a_Um[g].dev_ptr(), a_Mu[g].dev_ptr(), a_Lambda[g].dev_ptr(), a_Rho[g].dev_ptr(), 0,
-				  dev_sg_str_x[g], dev_sg_str_y[g], dev_sg_str_z[g], mGridSize[g], mDt, stream0() ) );
-      else
-      {
-	 // curvilinear grid under the topography: rhs4sgcurv + predictor (no GPU path in the reference)
-	 double* lu = lu_scratch( this, g );
-	 B200( sw4b200_rhs4sgcurv( Sarray::m_corder, BOUNDS( g ), a_U[g].dev_ptr(), a_Mu[g].dev_ptr(), a_Lambda[g].dev_ptr(),
-				   mMetric.dev_ptr(), mJ.dev_ptr(), lu, m_onesided[g], dev_sg_str_x[g], dev_sg_str_y[g], stream0() ) );
-	 B200( sw4b200_predfort( Sarray::m_corder, BOUNDS( g ), a_Up[g].dev_ptr(), a_U[g].dev_ptr(), a_Um[g].dev_ptr(), lu, 0,
-				 a_Rho[g].dev_ptr(), dt2, stream0() ) );
-      }
-      inject( this, g, a_Up[g].dev_ptr(), a_Rho[g].dev_ptr(), dt2 );
+      g_sUp[g] = &a_Up[g]; g_sU[g] = &a_U[g];
+      B200( sw4b200_grid_predictor_dev( g_grid[g], 0, g_src_built ? g_src[g].d_f : 0 ) );
    }
+   g_corr_done = false;
 }
 
-void EW::evalDpDmInTimeCU( vector<Sarray>& a_Up, vector<Sarray>& a_U, vector<Sarray>& a_Um, vector<Sarray>& a_Uacc, int st )
-{
-   (void)st;
-   for( int g = 0; g < mNumberOfGrids; g++ )
-      B200( sw4b200_dpdmtfort( BOUNDS( g ), a_Up[g].dev_ptr(), a_U[g].dev_ptr(), a_Um[g].dev_ptr(), a_Uacc[g].dev_ptr(),
-			       1.0 / ( mDt * mDt ), stream0() ) );
-}
+// the acceleration is stored by the predictor pass (Cartesian grids) or formed inside the corrector phase (curvilinear grid)
+void EW::evalDpDmInTimeCU( vector<Sarray>&, vector<Sarray>&, vector<Sarray>&, vector<Sarray>&, int ) {}
 
-// fused rhs4sg + corrector on the stored acceleration: replaces RHSCorrCU_boundary + RHSCorrCU_center (EW_cuda.C:1325-1410)
 void EW::RHSCorrCU_boundary( vector<Sarray>&, vector<Sarray>&, vector<Sarray>&, vector<Sarray>&, vector<Sarray>&,
 			     vector<Sarray>&, int ) {}
 void EW::RHSCorrCU_center( vector<Sarray>& a_Up, vector<Sarray>& a_Uacc, vector<Sarray>& a_Mu, vector<Sarray>& a_Lambda,
 			   vector<Sarray>& a_Rho, vector<Sarray>& a_F, int st )
 {
-   (void)a_F; (void)st;
-   const double dt4 = mDt * mDt * mDt * mDt;
+   (void)a_Up; (void)a_Uacc; (void)a_Mu; (void)a_Lambda; (void)a_Rho; (void)a_F; (void)st;
    for( int g = 0; g < mNumberOfGrids; g++ )
-   {
-      if( g < mNumberOfCartesianGrids )
-	 B200( sw4b200_rhs4_corr_acc( Sarray::m_corder, BOUNDS( g ), m_global_nz[g], m_onesided[g], a_Up[g].dev_ptr(),
-				      a_Uacc[g].dev_ptr(), a_Mu[g].dev_ptr(), a_Lambda[g].dev_ptr(), a_Rho[g].dev_ptr(), 0,
-				      dev_sg_str_x[g], dev_sg_str_y[g], dev_sg_str_z[g], mGridSize[g], mDt, stream0() ) );
-      else
-      {
-	 double* lu = lu_scratch( this, g );
-	 B200( sw4b200_rhs4sgcurv( Sarray::m_corder, BOUNDS( g ), a_Uacc[g].dev_ptr(), a_Mu[g].dev_ptr(), a_Lambda[g].dev_ptr(),
-				   mMetric.dev_ptr(), mJ.dev_ptr(), lu, m_onesided[g], dev_sg_str_x[g], dev_sg_str_y[g], stream0() ) );
-	 B200( sw4b200_corrfort( Sarray::m_corder, BOUNDS( g ), a_Up[g].dev_ptr(), lu, 0, a_Rho[g].dev_ptr(), dt4, stream0() ) );
-      }
-      inject( this, g, a_Up[g].dev_ptr(), a_Rho[g].dev_ptr(), dt4 / 12 );
-   }
+      B200( sw4b200_grid_corrector_dev( g_grid[g], 0, g_src_built ? g_src[g].d_f : 0 ) ); // (the table holds F_tt now: ForceCU(t,tt))
+   g_corr_done = true;
 }
 
-// supergrid damping: replaces addSuperGridDampingCU_upper_boundary + _center (EW_cuda.C:1418-1510)
+// supergrid damping is part of the corrector phase (box-decomposed: only where some damping coefficient is non-zero)
 void EW::addSuperGridDampingCU_upper_boundary( vector<Sarray>&, vector<Sarray>&, vector<Sarray>&, vector<Sarray>&, int ) {}
-void EW::addSuperGridDampingCU_center( vector<Sarray>& a_Up, vector<Sarray>& a_U, vector<Sarray>& a_Um, vector<Sarray>& a_Rho, int st )
-{
-   addSuperGridDampingCU( a_Up, a_U, a_Um, a_Rho, st );
-}
+void EW::addSuperGridDampingCU_center( vector<Sarray>&, vector<Sarray>&, vector<Sarray>&, vector<Sarray>&, int ) {}
+// (the unfused operator on caller-owned arrays, for hosts that sequence the step themselves)
 void EW::addSuperGridDampingCU( vector<Sarray>& a_Up, vector<Sarray>& a_U, vector<Sarray>& a_Um, vector<Sarray>& a_Rho, int st )
 {
    (void)st;
@@ -430,38 +496,40 @@ void EW::cartesian_bc_forcingCU( float_sw4 t, vector<float_sw4**>& a_BCForcing, 
    bool any = false;
    for( int g = 0; g < mNumberOfGrids && !any; g++ )
       for( int side = 0; side < 6; side++ ) any = any || ( m_point_source_test && m_bcType[g][side] == bDirichlet );
-   if( !any ) return; // the device copies hold the zeros uploaded by copy_bcforcing_arrays_to_device
+   if( !any ) return; // the grid blocks hold the zeros they were created with
    cartesian_bc_forcing( t, a_BCForcing, a_sources );
    for( int g = 0; g < mNumberOfGrids; g++ )
       for( int side = 0; side < 6; side++ )
-	 if( m_bcType[g][side] == bDirichlet && dev_BCForcing[g][side] )
-	    B200( sw4b200_memcpy_h2d( dev_BCForcing[g][side], a_BCForcing[g][side],
-				      3 * (size_t)m_NumberOfBCPoints[g][side] * sizeof( double ), stream0() ) );
-   B200( sw4b200_sync_stream( 0 ) );
+	 if( m_bcType[g][side] == bDirichlet && a_BCForcing[g][side] )
+	 {
+	    char name[16];
+	    snprintf( name, sizeof( name ), "bforce%d", side );
+	    if( sw4b200_grid_array_size( g_grid[g], name ) == 3 * (size_t)m_NumberOfBCPoints[g][side] )
+	       B200( sw4b200_grid_upload( g_grid[g], name, a_BCForcing[g][side] ) );
+	 }
 }
 
 // replaces enforceBCCU (EW_cuda.C:2070) and adds what EW::enforceBC does for the curvilinear grid (EW.C:3477-3501)
 void EW::enforceBCCU( vector<Sarray>& a_U, vector<Sarray>& a_Mu, vector<Sarray>& a_Lambda, float_sw4 t,
 		      vector<float_sw4**>& a_BCForcing, int st )
 {
-   (void)t; (void)a_BCForcing; (void)st;
+   (void)a_U; (void)a_Mu; (void)a_Lambda; (void)a_BCForcing; (void)st;
+   for( int g = 0; g < mNumberOfGrids; g++ ) B200( sw4b200_grid_enforce_bc( g_grid[g] ) );
+   if( topographyExists() )
+      B200( sw4b200_grid_enforce_cart_topo( g_grid[mNumberOfCartesianGrids - 1], g_grid[mNumberOfGrids - 1] ) );
+   if( !g_corr_done ) return;
+   // The step is complete.  The host reads the reference's device arrays in two places only: a check point about to be
+   // written (U and Up, EW.C:2778-2791) and the error norm after the last step (the array that holds Up now is U after
+   // cycleSolutionArrays, EW.C:2886-2888).  Refresh them from the grid blocks exactly then.
+   const int cycle = (int)floor( ( g_t_step - mTstart ) / mDt + 0.5 ) + 1; // currentTimeStep of the reference's loop
+   bool need_up = cycle >= mNumberOfTimeSteps, need_u = false;
+   for( size_t c = 0; c < m_check_points.size(); c++ )
+      if( CheckPointPeek::due( m_check_points[c], t, cycle, mDt ) ) need_up = need_u = true;
+   if( m_checkfornan ) need_up = true;
    for( int g = 0; g < mNumberOfGrids; g++ )
    {
-      int bc[6];
-      for( int s = 0; s < 6; s++ ) bc[s] = (int)m_bcType[g][s];
-      B200( sw4b200_bcfortsg( Sarray::m_corder, BOUNDS( g ), m_BndryWindow[g], m_global_nx[g], m_global_ny[g], m_global_nz[g],
-			      a_U[g].dev_ptr(), mGridSize[g], bc, a_Mu[g].dev_ptr(), a_Lambda[g].dev_ptr(),
-			      (const double* const*)dev_BCForcing[g], dev_sg_str_x[g], dev_sg_str_y[g], stream0() ) );
-      if( topographyExists() && g == mNumberOfGrids - 1 && m_bcType[g][4] == bStressFree )
-	 B200( sw4b200_freesurfcurvisg( Sarray::m_corder, BOUNDS( g ), m_global_nz[g], 5, a_U[g].dev_ptr(), a_Mu[g].dev_ptr(),
-					a_Lambda[g].dev_ptr(), mMetric.dev_ptr(), dev_BCForcing[g][4], dev_sg_str_x[g],
-					dev_sg_str_y[g], stream0() ) );
-   }
-   if( topographyExists() )
-   {
-      const int g = mNumberOfCartesianGrids - 1, gc = mNumberOfGrids - 1;
-      B200( sw4b200_enforce_cart_topo( Sarray::m_corder, a_U[g].dev_ptr(), BOUNDS( g ), a_U[gc].dev_ptr(), m_kStart[gc], m_kEnd[gc],
-				       stream0() ) );
+      if( need_up ) export_field( g, "Up", *g_sUp[g] );
+      if( need_u ) export_field( g, "U", *g_sU[g] );
    }
 }
 
@@ -553,7 +621,7 @@ void EW::extractRecordDataCU( int nt, int* mode, int* i0v, int* j0v, int* k0v, i
 	    exit( 1 );
 	 }
 	 const int g = s->m_grid0;
-	 const long long ni = m_iEnd[g] - m_iStart[g] + 1, nj = m_jEnd[g] - m_jStart[g] + 1;
+	 const long long ni = sw4b200_grid_row_pitch( g_grid[g] ), nj = m_jEnd[g] - m_jStart[g] + 1; // (device rows may be padded)
 	 idx[g].push_back( ( s->m_i0 - m_iStart[g] ) + ni * ( s->m_j0 - m_jStart[g] ) + ni * nj * ( s->m_k0 - m_kStart[g] ) );
 	 station[g].push_back( tsnr++ );
       }
@@ -574,9 +642,11 @@ void EW::extractRecordDataCU( int nt, int* mode, int* i0v, int* j0v, int* k0v, i
       const int n = (int)idx[g].size();
       goff[g] = off;
       if( n == 0 ) continue;
-      const size_t npts = (size_t)( m_iEnd[g] - m_iStart[g] + 1 ) * ( m_jEnd[g] - m_jStart[g] + 1 ) * ( m_kEnd[g] - m_kStart[g] + 1 );
-      B200( sw4b200_gather_points( Sarray::m_corder, npts, g_up[g], n, d_idx[g], urec_devmem + off, stream0() ) );
-      B200( sw4b200_gather_points( Sarray::m_corder, npts, g_um[g], n, d_idx[g], urec_devmem + off + 3 * n, stream0() ) );
+      const size_t npts = (size_t)sw4b200_grid_row_pitch( g_grid[g] ) * ( m_jEnd[g] - m_jStart[g] + 1 ) * ( m_kEnd[g] - m_kStart[g] + 1 );
+      B200( sw4b200_gather_points( Sarray::m_corder, npts, (const double*)sw4b200_grid_device_ptr( g_grid[g], "Up" ), n, d_idx[g],
+				   urec_devmem + off, stream0() ) );
+      B200( sw4b200_gather_points( Sarray::m_corder, npts, (const double*)sw4b200_grid_device_ptr( g_grid[g], "Um" ), n, d_idx[g],
+				   urec_devmem + off + 3 * n, stream0() ) );
       off += 6 * n;
    }
    B200( sw4b200_memcpy_d2h( h.data(), urec_devmem, off * sizeof( double ), stream0() ) );

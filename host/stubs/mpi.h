@@ -53,6 +53,9 @@ struct MPI_Status { int MPI_SOURCE, MPI_TAG, MPI_ERROR; };
 namespace sw4b200_mpistub {
 struct Msg { int tag; std::vector<char> data; };
 inline std::vector<Msg>& mailbox() { static std::vector<Msg> m; return m; }
+/* receives posted before their message was sent (Parallel_IO::write_array posts MPI_Irecv, then MPI_Send to itself) */
+struct PendingRecv { void* buf; size_t nbytes; int tag; bool done; };
+inline std::vector<PendingRecv>& pending() { static std::vector<PendingRecv> p; return p; }
 struct VecType { int count, blocklen, stride; MPI_Datatype base; };
 inline std::vector<VecType>& vtypes() { static std::vector<VecType> v; return v; }
 inline size_t type_size(MPI_Datatype t)
@@ -124,6 +127,18 @@ inline int MPI_Type_commit( MPI_Datatype* ) { return MPI_SUCCESS; }
 inline int MPI_Send( const void* buf, int n, MPI_Datatype t, int dest, int tag, MPI_Comm )
 {
    if( dest == MPI_PROC_NULL ) return MPI_SUCCESS;
+   {
+      std::vector<sw4b200_mpistub::PendingRecv>& pr = sw4b200_mpistub::pending();
+      for( size_t i=0; i<pr.size(); i++ )
+	 if( !pr[i].done && ( pr[i].tag == MPI_ANY_TAG || pr[i].tag == tag ) )
+	 {
+	    size_t nb = n*sw4b200_mpistub::type_size(t);
+	    if( pr[i].nbytes < nb ) nb = pr[i].nbytes;
+	    memcpy( pr[i].buf, buf, nb );
+	    pr[i].done = true;
+	    return MPI_SUCCESS;
+	 }
+   }
    sw4b200_mpistub::Msg m; m.tag = tag;
    m.data.assign( (const char*)buf, (const char*)buf + n*sw4b200_mpistub::type_size(t) );
    sw4b200_mpistub::mailbox().push_back( m );
@@ -153,10 +168,25 @@ inline int MPI_Irecv( void* buf, int n, MPI_Datatype t, int src, int tag, MPI_Co
 {
    *r = 0;
    if( src == MPI_PROC_NULL ) return MPI_SUCCESS;
-   return MPI_Recv( buf, n, t, src, tag, c, 0 );
+   std::vector<sw4b200_mpistub::Msg>& mb = sw4b200_mpistub::mailbox();
+   for( size_t i=0; i<mb.size(); i++ )
+      if( tag == MPI_ANY_TAG || mb[i].tag == tag ) return MPI_Recv( buf, n, t, src, tag, c, 0 );
+   /* not sent yet: completed by the matching MPI_Send */
+   sw4b200_mpistub::PendingRecv p = { buf, n*sw4b200_mpistub::type_size(t), tag, false };
+   sw4b200_mpistub::pending().push_back( p );
+   *r = (int)sw4b200_mpistub::pending().size();
+   return MPI_SUCCESS;
 }
-inline int MPI_Wait( MPI_Request*, MPI_Status* ) { return MPI_SUCCESS; }
-inline int MPI_Waitall( int, MPI_Request*, MPI_Status* ) { return MPI_SUCCESS; }
+inline int MPI_Wait( MPI_Request* r, MPI_Status* )
+{
+   if( r && *r > 0 && *r <= (int)sw4b200_mpistub::pending().size() && !sw4b200_mpistub::pending()[*r-1].done )
+   {
+      fprintf( stderr, "MPI stub: MPI_Wait on a receive whose message was never sent (tag %d)\n", sw4b200_mpistub::pending()[*r-1].tag );
+      exit(3);
+   }
+   return MPI_SUCCESS;
+}
+inline int MPI_Waitall( int n, MPI_Request* r, MPI_Status* ) { for( int i=0; i<n; i++ ) MPI_Wait( r+i, 0 ); return MPI_SUCCESS; }
 inline int MPI_Sendrecv( const void* sb, int sn, MPI_Datatype st, int dest, int stag,
 			 void* rb, int rn, MPI_Datatype rt, int src, int rtag, MPI_Comm c, MPI_Status* status )
 {

@@ -52,3 +52,75 @@ def test_reference_program_topography_stations(tmp_path):
         gold = station(os.path.join(HERE, "golden", "curvilinear-output", name))
         assert mine.shape == gold.shape
         assert np.abs(mine[:, 1:] - gold[:, 1:]).max() <= 1e-10 * np.abs(gold[:, 1:]).max(), name
+
+
+def timing_summary(out):
+    """(total seconds of steps 2..n, columns) from the program's `developer reporttiming=1` summary (EW.C:5317-5358)"""
+    lines = out.splitlines()
+    for n, l in enumerate(lines):
+        if l.strip().startswith("Total") and "Scheme" in l:
+            cols = []
+            for tok in lines[n + 1].split():
+                try:
+                    cols.append(float(tok))
+                except ValueError:
+                    break
+            return cols
+    return None
+
+
+@needs_exe
+@pytest.mark.parametrize("name,npts,nsteps", [("LOH.1-h100", 301 * 301 * 171, 536), ("LOH.1-h50", 601 * 601 * 341, 1072)])
+def test_reference_program_loh1_station(tmp_path, name, npts, nsteps):
+    """config 3: tests/loh1/LOH.1-h{100,50}.in through the reference's own main() on the grid-block kernels (odd ni: rows
+    padded on the device, TMA kernels); the station file the reference's TimeSeries writes must match the reference's golden
+    sta10.txt; the program's own timers give the solver rate"""
+    out = run(name + ".in", str(tmp_path))
+    f = [p for p in tmp_path.rglob("sta10.txt")]
+    assert f, out[-2000:]
+    mine = station(str(f[0]))
+    gold = station(os.path.join(HERE, "golden", "loh1-%s-sta10" % name.split("-")[1], "sta10.txt"))
+    assert mine.shape == gold.shape
+    scale = np.abs(gold[:, 1:4]).max()
+    err = np.abs(mine[:, 1:4] - gold[:, 1:4]).max() / scale
+    cols = timing_summary(out)
+    rate = npts * (nsteps - 1) / cols[0] / 1e9 if cols else float("nan")
+    print("%s through the C++ host: station rel. diff %.3g; solver %.3f s for steps 2..%d = %.2f Gpts/s (scheme %.3f, supergrid %.3f, bc %.3f)"
+          % (name, err, cols[0], nsteps, rate, cols[3], cols[4], cols[2]))
+    assert err < 1e-9
+
+
+CHK_BASE = """fileio verbose=1 path=%s
+grid x=2.4 y=2.0 z=1.6 h=0.04
+time t=0.6
+testpointsource rho=1 cp=1.6 cs=0.8 halfspace=1
+supergrid gp=10
+source x=1.2 y=1.0 z=0.6 Mxx=1 Myy=1 Mzz=1 Mxy=0 Mxz=0 Myz=0 t0=0 freq=1 type=C6SmoothBump
+developer checkfornan=0 cfl=1.3 reporttiming=0 corder=0
+"""
+
+
+@needs_exe
+def test_reference_program_checkpoint_restart(tmp_path):
+    """f4: check point / restart of a device-resident run in the reference's file format, through the reference's own CheckPoint
+    class (CheckPoint.C:251-370, EW.C:2778-2791, 2403-2415; corder=0: the reference's extract_subarray addresses (c,i,j,k)).
+    The run restarted from the file written at cycle 10 must end with the error norms of the uninterrupted run."""
+    def go(tag, extra):
+        d = tmp_path / tag
+        d.mkdir()
+        inp = d / "run.in"
+        inp.write_text(CHK_BASE % (str(d / "out")) + extra)
+        r = subprocess.run([EXE, str(inp)], cwd=str(d), capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+        err = [p for p in d.rglob("PointSourceErr.txt")]
+        assert err, r.stdout[-2000:]
+        return [float(x) for x in open(err[0]).read().split()], d, r.stdout
+    full, _, _ = go("full", "")
+    _, d1, out1 = go("first", "checkpoint cycle=10 file=chk\n")
+    files = [p for p in d1.rglob("*.sw4checkpoint")]
+    assert len(files) == 1, out1[-2000:]
+    again, _, out2 = go("second", "restart file=%s\n" % str(files[0]))
+    assert "reading check point" in out2
+    assert full[1] > 0
+    for a, b in zip(again, full):
+        assert abs(a - b) <= 1e-12 * abs(b), (again, full)
