@@ -131,6 +131,11 @@ class quiet_stdout:
 
     def __exit__(self, *a):
         sys.stdout.flush()
+        try:                                    # C stdio buffers too (NCCL's version banner is a printf)
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
         os.dup2(self.saved, 1)
         os.close(self.saved)
 
@@ -317,7 +322,8 @@ def main_ours(a):
         for dj in range(-3, 3):
             for dk in range(-3, 3):
                 prob.add_point_force(ci + di, cj + dj, ck + dk, rng.uniform(-1e12, 1e12, 3), freq=2.0, t0=0.0)
-    S.lib.comm_init(rank, N)          # the library's own NCCL communicator for the halo exchange (csrc/exchange.cu)
+    with quiet_stdout():              # (NCCL prints its version banner on stdout when a communicator is created)
+        S.lib.comm_init(rank, N)      # the library's own NCCL communicator for the halo exchange (csrc/exchange.cu)
     blk = prob.make_block(device=local, rank=rank, nranks=N, comm=True)
     nrec = 0
     if rank == 0:

@@ -42,7 +42,23 @@ def newer(target, *deps):
     return os.path.exists(target) and all(os.path.getmtime(d) <= os.path.getmtime(target) for d in deps)
 
 
+def build_slab_driver(verbose=True):
+    """host/_build/slab_driver: the C++ multi-GPU z-slab driver on the C-ABI (plain g++, needs neither nvcc nor the reference)"""
+    os.makedirs(OUT, exist_ok=True)
+    src = os.path.join(HERE, "slab_driver.C")
+    exe = os.path.join(OUT, "slab_driver")
+    lib = os.path.join(LIBDIR, "libsw4b200.so")
+    if not os.path.exists(lib):
+        raise SystemExit("host build: libsw4b200.so is not built")
+    if not newer(exe, src, os.path.join(ROOT, "include", "sw4b200.h"), lib):
+        run(["/usr/bin/g++", "-O2", "-std=c++17", "-o", exe, src, "-L", LIBDIR, "-lsw4b200", "-Wl,-rpath,$ORIGIN/../../sw4lite_b200", "-lpthread"])
+    if verbose:
+        print("host: built", exe)
+    return True
+
+
 def build(verbose=True):
+    build_slab_driver(verbose)
     if not os.path.isdir(SRC):
         if verbose:
             print("host: %s not present, keeping the prebuilt %s" % (SRC, EXE))

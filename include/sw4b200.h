@@ -282,6 +282,12 @@ int sw4b200_grid_corrector_dev( sw4b200_grid* g, int part, const double* d_ftt )
 int sw4b200_comm_unique_id( void* out128 );
 int sw4b200_comm_init( int rank, int nranks, const void* id128 );
 int sw4b200_comm_finalize( void );
+/* host values reduced over the ranks, in place (what the reference does with MPI_Allreduce for dt and the error norms,
+ * EW.C:5134, 4606-4608): op 0 = max, 1 = sum, 2 = min.  Synchronises the device. */
+int sw4b200_comm_allreduce( double* h_values, int n, int op );
+/* device timer (CUDA events on library stream 0) */
+int sw4b200_timer_start( void );
+int sw4b200_timer_stop_ms( double* ms );
 int sw4b200_grid_set_neighbours( sw4b200_grid* g, int rank_lo, int rank_hi );   /* -1: no neighbour on that face */
 int sw4b200_grid_exchange_begin( sw4b200_grid* g, int with_acc );              /* after the face rows (part 1)   */
 int sw4b200_grid_exchange_end( sw4b200_grid* g );                              /* before the boundary conditions  */

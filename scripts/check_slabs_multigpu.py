@@ -20,7 +20,8 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nz = int(sys.argv[1]) if len(sys.argv) > 1 else 24 * world
-    prob = CartesianProblem(70, 45, nz, h=100.0, gp=7, corder=1, layers=[(1500.0, 6000.0, 3464.0, 2700.0)])
+    nx = int(sys.argv[2]) if len(sys.argv) > 2 else 70
+    prob = CartesianProblem(nx, 45, nz, h=100.0, gp=7, corder=1, layers=[(1500.0, 6000.0, 3464.0, 2700.0)])
     prob.add_point_force(30, 20, 8, (1e12, 2e12, -1e12), freq=2.0)
     prob.add_point_force(40, 25, nz // 2 + 1, (-2e12, 1e12, 1e12), freq=3.0)
     prob.add_point_force(35, 22, nz - 9, (1e12, 1e12, 1e12), freq=2.5)

@@ -18,6 +18,7 @@ int measure_fp64_peak( double* tflops, double* fma_per_s, cudaStream_t st ); // 
 int comm_unique_id( void* out128 );
 int comm_init( int rank, int nranks, const void* id128 );
 int comm_finalize();
+int comm_allreduce( double* v, int n, int op, cudaStream_t st );
 int comm_rank();
 int comm_size();
 int exchange_field( const Block& b, double* field, int peer_lo, int peer_hi, cudaStream_t st );
@@ -1250,6 +1251,32 @@ int sw4b200_comm_init( int rank, int nranks, const void* id128 )
    return comm_init( rank, nranks, id128 );
 }
 int sw4b200_comm_finalize( void ) { return comm_finalize(); }
+int sw4b200_comm_allreduce( double* h_values, int n, int op )
+{
+   if( need_init() ) return 1;
+   CUDA_OK( cudaDeviceSynchronize() );
+   return comm_allreduce( h_values, n, op, g_streams[3] );
+}
+// device timer on library stream 0 (the blocks' default stream): CUDA events, as the benchmark contract asks
+static cudaEvent_t g_timer[2] = { 0, 0 };
+int sw4b200_timer_start( void )
+{
+   if( need_init() ) return 1;
+   for( int e = 0; e < 2; e++ )
+      if( !g_timer[e] ) CUDA_OK( cudaEventCreate( &g_timer[e] ) );
+   CUDA_OK( cudaEventRecord( g_timer[0], g_streams[0] ) );
+   return 0;
+}
+int sw4b200_timer_stop_ms( double* ms )
+{
+   if( need_init() || !g_timer[1] ) return set_error( "timer_stop: the timer was not started" );
+   CUDA_OK( cudaEventRecord( g_timer[1], g_streams[0] ) );
+   CUDA_OK( cudaEventSynchronize( g_timer[1] ) );
+   float f = 0;
+   CUDA_OK( cudaEventElapsedTime( &f, g_timer[0], g_timer[1] ) );
+   *ms = f;
+   return 0;
+}
 int sw4b200_grid_set_neighbours( sw4b200_grid* g, int rank_lo, int rank_hi )
 {
    if( ( rank_lo >= 0 ) != ( g->d.halo_lo != 0 ) || ( rank_hi >= 0 ) != ( g->d.halo_hi != 0 ) )

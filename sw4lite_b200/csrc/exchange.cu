@@ -28,6 +28,7 @@ struct NcclApi
    decltype( &ncclCommDestroy ) CommDestroy;
    decltype( &ncclSend ) Send;
    decltype( &ncclRecv ) Recv;
+   decltype( &ncclAllReduce ) AllReduce;
    decltype( &ncclGroupStart ) GroupStart;
    decltype( &ncclGroupEnd ) GroupEnd;
    decltype( &ncclGetErrorString ) GetErrorString;
@@ -52,6 +53,7 @@ int nccl_load()
    SW4_SYM( CommDestroy, "ncclCommDestroy" )
    SW4_SYM( Send, "ncclSend" )
    SW4_SYM( Recv, "ncclRecv" )
+   SW4_SYM( AllReduce, "ncclAllReduce" )
    SW4_SYM( GroupStart, "ncclGroupStart" )
    SW4_SYM( GroupEnd, "ncclGroupEnd" )
    SW4_SYM( GetErrorString, "ncclGetErrorString" )
@@ -95,6 +97,23 @@ int comm_finalize()
 {
    if( g_comm ) { g_nccl.CommDestroy( g_comm ); g_comm = 0; }
    g_rank = 0; g_nranks = 1;
+   return 0;
+}
+
+// small host-value reductions over the ranks (dt, error norms, timings: EW.C:5134, 4606-4608): op 0 = max, 1 = sum, 2 = min
+int comm_allreduce( double* v, int n, int op, cudaStream_t st )
+{
+   if( g_nranks == 1 ) return 0;
+   if( !g_comm ) return set_error( "comm_allreduce: sw4b200_comm_init has not been called" );
+   double* d = 0;
+   if( cudaMalloc( (void**)&d, n * sizeof( double ) ) != cudaSuccess ) return set_error( "comm_allreduce: cudaMalloc failed" );
+   cudaMemcpyAsync( d, v, n * sizeof( double ), cudaMemcpyHostToDevice, st );
+   const ncclRedOp_t o = op == 0 ? ncclMax : ( op == 1 ? ncclSum : ncclMin );
+   ncclResult_t r = g_nccl.AllReduce( d, d, n, ncclDouble, o, g_comm, st );
+   cudaMemcpyAsync( v, d, n * sizeof( double ), cudaMemcpyDeviceToHost, st );
+   cudaStreamSynchronize( st );
+   cudaFree( d );
+   if( r != ncclSuccess ) return set_error( "ncclAllReduce: %s", g_nccl.GetErrorString( r ) );
    return 0;
 }
 

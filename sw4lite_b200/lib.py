@@ -96,6 +96,9 @@ SIGNATURES = {
     "sw4b200_comm_unique_id": (I, [VP]),
     "sw4b200_comm_init": (I, [I, I, VP]),
     "sw4b200_comm_finalize": (I, []),
+    "sw4b200_comm_allreduce": (I, [c_dp, I, I]),
+    "sw4b200_timer_start": (I, []),
+    "sw4b200_timer_stop_ms": (I, [c_dp]),
     "sw4b200_grid_set_neighbours": (I, [VP, I, I]),
     "sw4b200_grid_exchange_begin": (I, [VP, I]),
     "sw4b200_grid_exchange_end": (I, [VP]),

@@ -124,3 +124,47 @@ def test_reference_program_checkpoint_restart(tmp_path):
     assert full[1] > 0
     for a, b in zip(again, full):
         assert abs(a - b) <= 1e-12 * abs(b), (again, full)
+
+
+SLAB_EXE = os.path.join(HERE, "..", "host", "_build", "slab_driver")
+
+
+@pytest.mark.skipif(not os.path.exists(SLAB_EXE), reason="host/_build/slab_driver not built")
+def test_cxx_slab_driver_matches_the_python_driver():
+    """the C++ z-slab driver (host/slab_driver.C: its own set-up in C++, the C-ABI phases, exchange entry points) on one GPU
+    against the Python driver on the same problem: same dt, same final wavefield (set-up formulas agree to rounding)"""
+    import json
+    from sw4lite_b200.setup import CartesianProblem
+    nx, ny, nz, steps, warm = 68, 36, 40, 4, 2
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0")
+    r = subprocess.run([SLAB_EXE, "--nx", str(nx), "--ny", str(ny), "--nzl", str(nz), "--steps", str(steps), "--warmup", str(warm),
+                        "--gp", "8", "--h", "100"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    prob = CartesianProblem(nx, ny, nz, h=100.0, gp=8, beta=0.02, corder=1, layers=[(0.6 * nz * 100.0, 6000.0, 3464.0, 2700.0)])
+    assert abs(out["dt"] - prob.dt) <= 1e-15 * prob.dt
+    lcg, M = 12345, (1 << 64) - 1
+    ci, cj, ck = nx // 2, ny // 2, max(8, min(nz // 2, nz - 8))
+    for di in range(-3, 3):
+        for dj in range(-3, 3):
+            for dk in range(-3, 3):
+                a = []
+                for c in range(3):
+                    lcg = (lcg * 6364136223846793005 + 1442695040888963407) & M
+                    a.append(((lcg >> 11) / 9007199254740992.0 * 2 - 1) * 1e12)
+                prob.add_point_force(ci + di, cj + dj, ck + dk, a, freq=2.0)
+    blk = prob.make_block()
+    ni, nj, nk = prob.ni, prob.nj, prob.nk
+    u = np.zeros((2, 3, nk, nj, ni))
+    for c in range(3):
+        for ph, phs in ((0, 0.0), (1, 0.013)):
+            fi = np.sin(0.11 * np.arange(ni) + 0.7 * c + phs); fj = np.cos(0.07 * np.arange(nj) + 0.3 * c)
+            fk = 1e-3 * np.sin(0.05 * (np.arange(nk) + prob.bounds[4]) + c + phs)
+            u[ph, c] = fk[:, None, None] * fj[None, :, None] * fi[None, None, :]
+    blk.upload("U", u[0].ravel()); blk.upload("Um", u[1].ravel())
+    for n in range(warm + steps):
+        blk.step(prob.forces(n * prob.dt), prob.forces(n * prob.dt, tt=True))
+    own = blk.download("U").reshape(3, nk, nj, ni)[:, 2:-2, 2:-2, 2:-2]
+    ss, mx = float((own ** 2).sum()), float(np.abs(own).max())
+    print("C++ slab driver vs Python: sum_sq %.15g / %.15g, max %.15g / %.15g" % (out["checksum"]["sum_sq"], ss, out["checksum"]["max_abs"], mx))
+    assert mx > 0 and abs(out["checksum"]["max_abs"] - mx) <= 1e-9 * mx and abs(out["checksum"]["sum_sq"] - ss) <= 1e-9 * ss
