@@ -42,7 +42,7 @@ static double psi0( double xi ) // SuperGrid::Psi0 (SuperGrid.C:170-192)
 {
    if( xi <= 0 ) return 0;
    if( xi >= 1 ) return 1;
-   return pow( xi, 6 ) * ( 462 - 1980 * xi + 3465 * xi * xi - 3080 * pow( xi, 3 ) + 1386 * pow( xi, 4 ) - 252 * pow( xi, 5 ) );
+   return xi * xi * xi * xi * xi * xi * ( 462 - 1980 * xi + 3465 * xi * xi - 3080 * xi * xi * xi + 1386 * xi * xi * xi * xi - 252 * xi * xi * xi * xi * xi );
 }
 struct Sg1d { std::vector<double> dc, str, co; };
 // dampingCoeff / stretching / cornerTaper at the coordinates x (SuperGrid.C:108-198), layers of `width` on the chosen sides

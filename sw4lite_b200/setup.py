@@ -11,7 +11,9 @@ from .solver import bStressFree, bSuperGrid, bProcessor, boundary_windows
 def _psi0(xi):
     """C5 polynomial taper, SuperGrid::Psi0 (SuperGrid.C:170-192)"""
     xi = np.asarray(xi, dtype=np.float64)
-    f = xi ** 6 * (462 - 1980 * xi + 3465 * xi ** 2 - 3080 * xi ** 3 + 1386 * xi ** 4 - 252 * xi ** 5)
+    # (products left to right, as the reference writes them: the stretching 1-(1-epsL)*psi amplifies the last bits of psi)
+    f = xi * xi * xi * xi * xi * xi * (462 - 1980 * xi + 3465 * xi * xi - 3080 * xi * xi * xi + 1386 * xi * xi * xi * xi
+                                       - 252 * xi * xi * xi * xi * xi)
     return np.where(xi <= 0, 0.0, np.where(xi >= 1, 1.0, f))
 
 

@@ -1,0 +1,70 @@
+"""Host-side set-up of the synthetic problems (sw4lite_b200/setup.py, mirrored in C++ by host/slab_driver.C) against the
+reference's own parser + setupRun (oracle/_ref): supergrid damping / stretching / corner-taper arrays
+(SuperGrid.C:108-198, EW.C:4671-4801), the time step (EW::computeDT, EW.C:5041-5066), boundary types, one-sided flags and
+windows (EW.C:4805-4867, 3347-3420), layered materials, and the z-slab decomposition rule (EW::decomp1d, EW.C:2963-2985)."""
+import os
+import numpy as np
+import pytest
+
+from oracle import refshim
+from sw4lite_b200.setup import CartesianProblem, supergrid_1d
+from sw4lite_b200.slabs import slab_range
+
+needs_ref = pytest.mark.skipif(not refshim.available(), reason="oracle/_ref/libsw4ref.so not present")
+
+
+def ref_problem(tmp_path, nx, ny, nz, h, gp, ztop):
+    txt = "\n".join([
+        "fileio path=%s verbose=0" % str(tmp_path / "out"),
+        "grid nx=%d ny=%d nz=%d h=%g" % (nx, ny, nz, h),
+        "time steps=5",
+        "developer checkfornan=0 reporttiming=0 corder=1 cfl=1.3",
+        "supergrid gp=%d" % gp,
+        "block vp=4000 vs=2000 r=2600",
+        "block vp=6000 vs=3464 r=2700 z1=%g" % ztop,
+        "source x=%g y=%g z=%g mxy=1e18 t0=0 freq=10 type=C6SmoothBump" % (0.5 * nx * h, 0.5 * ny * h, 0.3 * nz * h), ""])
+    f = tmp_path / "setup.in"
+    f.write_text(txt)
+    return refshim.RefEW(str(f), str(tmp_path))
+
+
+@needs_ref
+@pytest.mark.parametrize("nx,ny,nz,gp", [(61, 50, 45, 12), (100, 72, 70, 30)])
+def test_cartesian_problem_equals_the_references_setup(tmp_path, nx, ny, nz, gp):
+    h = 25.0
+    ztop = 0.6 * nz * h
+    ew = ref_problem(tmp_path, nx, ny, nz, h, gp, ztop)
+    prob = CartesianProblem(nx, ny, nz, h=h, vp=4000.0, vs=2000.0, rho=2600.0, gp=gp, beta=ew.beta, corder=1,
+                            layers=[(ztop, 6000.0, 3464.0, 2700.0)])
+    G = ew.grids[0]
+    assert G.bounds == prob.bounds and (G.nx, G.ny, G.nz) == (nx, ny, nz)
+    assert list(G.onesided) == list(prob.onesided) and list(G.bctype) == list(prob.bctype)
+    assert np.array_equal(G.wind, prob.wind)
+    assert ew.sgorder == 4 and ew.usesg == 1
+    for name in ("strx", "stry", "strz", "dcx", "dcy", "dcz", "cox", "coy", "coz"):
+        a, b = np.array(ew.array(name, 0)), getattr(prob, name)
+        assert a.shape == b.shape
+        assert np.max(np.abs(a - b)) <= 4e-16 * max(1.0, np.max(np.abs(a))), name
+    # the reference rounds dt so that an integer number of steps reaches t; with `time steps=` it keeps the CFL value
+    assert abs(ew.dt - prob.dt) <= 1e-15 * prob.dt
+    for name, mine in (("mu", prob.mu), ("lambda", prob.la), ("rho", prob.rho)):
+        ref = np.array(ew.array(name, 0))
+        assert np.max(np.abs(ref - mine)) <= 1e-15 * np.max(np.abs(ref)), name
+
+
+def test_supergrid_profiles_are_tapers():
+    x = np.arange(-2, 103) * 10.0
+    dc, stretch, corner = supergrid_1d(x, True, True, 0.0, 1000.0, 300.0)
+    assert dc[50] == 0 and stretch[50] == 1 and corner[50] == 1            # untouched interior
+    assert np.all(stretch > 0) and stretch.min() >= 1e-4 - 1e-18 and corner.min() >= 0.33 - 1e-12
+    assert np.all(dc >= 0) and dc[0] > 0 and dc[-1] > 0 and np.all(dc[32:73] == 0)
+
+
+@pytest.mark.parametrize("nz,n", [(128, 8), (341, 8), (1900, 8), (41, 3), (24, 2)])
+def test_slabs_tile_the_grid(nz, n):
+    owned = [slab_range(nz, r, n) for r in range(n)]
+    assert owned[0][0] == 1 and owned[-1][1] == nz
+    for a, b in zip(owned[:-1], owned[1:]):
+        assert b[0] == a[1] + 1
+    sizes = [b - a + 1 for a, b in owned]
+    assert max(sizes) - min(sizes) <= 5      # decomp1d balances the padded blocks; the end slabs own up to 2+2 more planes
