@@ -39,11 +39,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
-    ap.add_argument("--config", default="sweep", choices=["sweep", "strong", "testil256", "host"],
+    ap.add_argument("--config", default="sweep", choices=["sweep", "strong", "testil256", "host", "loh1-h100", "loh1-h50"],
                     help="sweep: weak-scaling sweep, nx x ny x nzl per GPU (BASELINE.json config 5, the default line); strong: nx x ny x "
                          "nz-total split over the GPUs (config 5, strong scaling); testil256: standalone rhs4sg on the reference "
                          "harness's 256^3 fields (config 2); host: the reference's own program (main, parser, set-up) on this "
-                         "repository's kernels, host/_build/sw4lite_b200, on a generated .in file")
+                         "repository's kernels, host/_build/sw4lite_b200, on a generated .in file; loh1-h100 / loh1-h50: the LOH.1 "
+                         "layer-over-half-space run of the reference (config 3), whole run, station checked against the golden file")
     ap.add_argument("--nz-total", type=int, default=256, help="--config strong: interior planes of the whole grid")
     ap.add_argument("--host-grid", default="640x640x320", help="grid of --config host and --impl reference-cuda")
     ap.add_argument("--nx", type=int, default=2048)
@@ -476,6 +477,125 @@ def main_ours(a):
         dist.destroy_process_group()
 
 
+def main_loh1(a):
+    """BASELINE.json config 3: LOH.1 (tests/loh1/LOH.1-h100.in / -h50.in) on N GPUs as z-slabs: the whole run (t = 0..9 s) is
+    timed, and the station trace must reproduce the reference's golden sta10.txt.  Set-up: CartesianProblem.loh1 (equal to the
+    reference's own set-up, tests/test_setup.py) + the discretised source of tests/golden/loh1-*-setup.npz."""
+    import torch
+    import torch.distributed as dist
+    import ctypes as C
+    import sw4lite_b200 as S
+    from sw4lite_b200.setup import CartesianProblem
+    from sw4lite_b200.slabs import SlabStepper
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = S.init(local)
+    with quiet_stdout():
+        S.lib.comm_init(rank, world)
+    tag = a.config.split("-")[1]
+    prob = CartesianProblem.loh1(100.0 if tag == "h100" else 50.0)
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "loh1-%s-setup.npz" % tag))
+    n = int(fx["nsteps"])
+    assert n == prob.nsteps and abs(float(fx["dt"]) - prob.dt) <= 1e-16
+    blk = prob.make_block(device=local, rank=rank, nranks=world, comm=True)
+    k0, k1 = blk.bounds[4] + 2, blk.bounds[5] - 2
+    sel = [m for m, p in enumerate(fx["ijk"]) if k0 <= p[2] <= k1]
+    if sel:
+        blk.set_source_points(fx["ijk"][sel])
+    f_all = fx["F0"][sel][None] * fx["g"][:, None, None]
+    ftt_all = fx["F0"][sel][None] * fx["gtt"][:, None, None]
+    rec = fx["rec"]
+    owner = bool(k0 <= rec[0][2] <= k1)
+    if owner:
+        blk.set_receiver_points(rec)
+    main = torch.cuda.ExternalStream(lib.sw4b200_stream(0))
+    stepper = SlabStepper(blk, None) if world > 1 else None
+
+    def zero_state():
+        pitch = lib.sw4b200_grid_row_pitch(blk.h)
+        nb = 3 * 8 * pitch * blk.nj * blk.nk
+        for name in ("U", "Um", "Up"):
+            S.lib.check(lib.sw4b200_memset_zero(C.c_void_p(blk.device_ptr(name)), nb, None))
+        S.lib.check(lib.sw4b200_sync_device())
+
+    # the slab stepper with the receiver sampled before the arrays rotate
+    def slab_step(s):
+        b = blk
+        f, ftt = (f_all[s], ftt_all[s]) if sel else (None, None)
+        b.predictor_part(1, f); b.begin_exchange(None, with_acc=True); b.predictor_part(2, f); b.end_exchange(None, with_acc=True)
+        b.enforce_bc()
+        b.corrector_part(1, ftt); b.begin_exchange(None); b.corrector_part(2, ftt); b.end_exchange(None)
+        b.enforce_bc()
+        if owner:
+            b.record_resident(s)
+        b.cycle()
+
+    def barrier():
+        S.lib.check(lib.sw4b200_sync_device())
+        if world > 1:
+            dist.barrier()
+        S.lib.check(lib.sw4b200_sync_device())
+
+    if world == 1:
+        blk.set_source_series(f_all, ftt_all)
+    # warm-up on the real problem, then back to the initial state (U = Um = 0)
+    for s in range(min(a.warmup, n)):
+        if world == 1:
+            blk.run(s, 1)
+        else:
+            slab_step(s)
+    zero_state()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = lib.sw4b200_kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(main)
+    if world == 1:
+        blk.run(0, n)
+    else:
+        for s in range(n):
+            slab_step(s)
+    e1.record(main)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.sw4b200_kernel_launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    err = -1.0
+    if owner:
+        trace = blk.fetch_records(0, n)[:, 0, :]
+        gold = np.array([l.split() for l in open(os.path.join(ROOT, "tests", "golden", "loh1-%s-sta10" % tag, "sta10.txt")) if not l.startswith("#")],
+                        dtype=np.float64)
+        scale = np.abs(gold[:, 1:4]).max()
+        err = float(np.abs(trace - gold[1:, 1:4]).max() / scale) if gold.shape[0] == n + 1 else float("inf")
+    if world > 1:
+        t = torch.tensor([ms, err], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, err = float(t[0].item()), float(t[1].item())
+    if rank == 0:
+        pts = prob.nx * prob.ny * prob.nz
+        gpts = pts * n / (ms * 1e-3) / 1e9
+        peak, _ = peaks()
+        line = {"metric": "grid-point updates/sec per timestep", "value": gpts, "unit": "Gpts/s", "n_gpus": world, "steps": n, "warmup": a.warmup,
+                "ms_per_step": ms / n, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "the reference's LOH.1 input (tests/loh1/LOH.1-%s.in)" % tag,
+                "config": {"workload": "LOH.1 layer over half-space, %dx%dx%d, h=%g, free surface + supergrid gp=30 on five sides, Gaussian moment "
+                                       "source, %d steps (t=9 s), z-slabs over %d GPU(s); whole run timed" % (prob.nx, prob.ny, prob.nz, prob.h, n, world),
+                           "grid": [prob.nx, prob.ny, prob.nz], "parallelism": "z-slab x%d" % world},
+                "solver_seconds": ms * 1e-3, "station_rel_diff_to_golden": err, "station_ok": bool(0 <= err < 1e-9),
+                "e2e": {"value": gpts, "unit": "Gpts/s", "h2d_bytes_per_step": 0 if world == 1 else int(2 * 3 * 8 * len(sel)), "d2h_bytes_per_step": 0,
+                        "note": "the run as a user makes it: source table in, station trace out after the last step (24 bytes per step, fetched once)"},
+                "gpu_launches": int(launches), "clocks": clocks, "step_frac_of_hbm": BYTES_PER_POINT_STEP * gpts / world / peak}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main_testil(a):
     """BASELINE.json config 2: the standalone rhs4sg kernel on the reference harness's analytic 256^3 fields
     (tests/testil/testil.C:97,209-227,411-420; rate on (n-4)^3 points and 666 flop per point as testil.C:380-390 prints)"""
@@ -586,5 +706,7 @@ if __name__ == "__main__":
         main_host(args)
     elif args.config == "testil256":
         main_testil(args)
+    elif args.config.startswith("loh1"):
+        main_loh1(args)
     else:
         main_ours(args)

@@ -255,6 +255,9 @@ int sw4b200_grid_corrector_part( sw4b200_grid* g, int part, const double* h_ftt 
 int sw4b200_grid_set_source_series( sw4b200_grid* g, int nsteps, const double* h_f, const double* h_ftt );
 int sw4b200_grid_run( sw4b200_grid* g, int first_step, int nsteps );
 int sw4b200_grid_fetch_records( sw4b200_grid* g, int first_step, int nsteps, double* h_out /* nsteps*3*nrec */ );
+/* the same device-resident record for drivers that sequence the phases themselves (z-slab runs): samples the receivers from
+ * the new solution of step `step` (call after the second sw4b200_grid_enforce_bc, before sw4b200_grid_cycle) */
+int sw4b200_grid_record_resident( sw4b200_grid* g, int step );
 /* layered media: fill scalar field `name` ("mu","lambda","rho") with h_kvalues[k-kfirst] on plane k
  * (what MaterialBlock produces for depth-only blocks, MaterialBlock.C) without a host copy of the field */
 int sw4b200_grid_fill_profile( sw4b200_grid* g, const char* name, const double* h_kvalues /* nk */ );

@@ -1327,25 +1327,42 @@ int sw4b200_grid_set_source_series( sw4b200_grid* g, int nsteps, const double* h
    return 0;
 }
 
+// room for the receiver samples of steps [0,nsteps) on the device
+static int reserve_records( sw4b200_grid* g, int nsteps )
+{
+   if( g->nrec == 0 || g->recser_steps >= nsteps ) return 0;
+   int cap = g->recser_steps > 0 ? 2 * g->recser_steps : 64;
+   if( cap < nsteps ) cap = nsteps;
+   double* nb = 0;
+   const size_t per = 3 * (size_t)g->nrec;
+   CUDA_OK( cudaMalloc( (void**)&nb, (size_t)cap * per * sizeof( double ) ) );
+   if( g->d_recser )
+   {
+      CUDA_OK( cudaMemcpyAsync( nb, g->d_recser, (size_t)g->recser_steps * per * sizeof( double ), cudaMemcpyDeviceToDevice, g->st ) );
+      CUDA_OK( cudaStreamSynchronize( g->st ) );
+      cudaFree( g->d_recser );
+   }
+   g->d_recser = nb;
+   g->recser_steps = cap;
+   return 0;
+}
+
+// receivers of the new solution (Up) of step `step` into the device-resident record, no host synchronisation (for drivers that
+// sequence the phases themselves, e.g. z-slab runs); sw4b200_grid_fetch_records reads them back
+int sw4b200_grid_record_resident( sw4b200_grid* g, int step )
+{
+   if( g->nrec == 0 ) return 0;
+   if( step < 0 ) return set_error( "grid_record_resident: negative step" );
+   if( reserve_records( g, step + 1 ) ) return 1;
+   return launch_gather_points( g->d.corder, g->b.npts, g->Up, g->nrec, g->d_recidx, g->d_recser + (size_t)step * 3 * g->nrec, g->st );
+}
+
 int sw4b200_grid_run( sw4b200_grid* g, int first_step, int nsteps )
 {
    if( g->nsrc > 0 && first_step + nsteps > g->series_steps )
       return set_error( "grid_run: steps [%d,%d) exceed the uploaded source series (%d steps)", first_step,
 			first_step + nsteps, g->series_steps );
-   if( g->nrec > 0 && g->recser_steps < first_step + nsteps )
-   {
-      double* nb = 0;
-      const size_t per = 3 * (size_t)g->nrec;
-      CUDA_OK( cudaMalloc( (void**)&nb, ( size_t )( first_step + nsteps ) * per * sizeof( double ) ) );
-      if( g->d_recser )
-      {
-	 CUDA_OK( cudaMemcpyAsync( nb, g->d_recser, (size_t)g->recser_steps * per * sizeof( double ), cudaMemcpyDeviceToDevice, g->st ) );
-	 CUDA_OK( cudaStreamSynchronize( g->st ) );
-	 cudaFree( g->d_recser );
-      }
-      g->d_recser = nb;
-      g->recser_steps = first_step + nsteps;
-   }
+   if( reserve_records( g, first_step + nsteps ) ) return 1;
    for( int s = first_step; s < first_step + nsteps; s++ )
    {
       if( predictor_part( g, 0, g->nsrc ? g->d_fser + (size_t)s * 3 * g->nsrc : 0 ) ) return 1;

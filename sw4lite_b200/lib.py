@@ -85,6 +85,7 @@ SIGNATURES = {
     "sw4b200_grid_set_source_series": (I, [VP, I, c_dp, c_dp]),
     "sw4b200_grid_run": (I, [VP, I, I]),
     "sw4b200_grid_fetch_records": (I, [VP, I, I, c_dp]),
+    "sw4b200_grid_record_resident": (I, [VP, I]),
     "sw4b200_grid_fill_profile": (I, [VP, C.c_char_p, c_dp]),
     "sw4b200_grid_set_stream": (I, [VP, I]),
     "sw4b200_grid_pack_halo": (I, [VP, I, I, VP, VP]),

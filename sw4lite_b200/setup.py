@@ -90,6 +90,25 @@ class CartesianProblem:
         self.dt = cfl * self.h / np.sqrt(np.max((4 * muk + lak) / rhk))
         self.sources = []  # (i,j,k, fx,fy,fz, freq, t0)
 
+    def set_end_time(self, tmax):
+        """`time t=`: the reference shortens dt so that a whole number of steps reaches tmax (EW.C:5138-5145)"""
+        self.nsteps = max(1, int(tmax / self.dt + 0.5))     # (rounded to the nearest integer: dt may grow slightly)
+        self.dt = tmax / self.nsteps
+        return self.nsteps
+
+    @classmethod
+    def loh1(cls, h, corder=1):
+        """the LOH.1 layer-over-half-space benchmark of the reference (tests/loh1/LOH.1-h100.in, -h50.in: BASELINE.json config 3):
+        30 km x 30 km x 17 km, free surface, supergrid gp=30 on the other five sides, 1 km layer over the half-space with the
+        averaged interface block at z=1000, t=9 s.  The discretised moment source and the receiver come from
+        tests/golden/loh1-h*-setup.npz (generated by the reference's own source discretisation)."""
+        nx = int(round(30000.0 / h)) + 1
+        nz = int(round(17000.0 / h)) + 1
+        prob = cls(nx, nx, nz, h=h, vp=4000.0, vs=2000.0, rho=2600.0, gp=30, cfl=1.3, beta=0.02, corder=corder,
+                   layers=[(999.0, 4630.76, 2437.56, 2650.0), (1001.0 + 1e-6, 6000.0, 3464.0, 2700.0)])
+        prob.set_end_time(9.0)
+        return prob
+
     @property
     def mu(self):
         return np.repeat(self.muk, self.ni * self.nj)

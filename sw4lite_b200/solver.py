@@ -149,6 +149,10 @@ class GridBlock:
             L.check(self.lib.sw4b200_grid_fetch_records(self.h, int(first_step), int(nsteps), _d(out)))
         return out[:, :self.nrec]
 
+    def record_resident(self, step):
+        """sample the receivers from the new solution of `step` into the device-resident record (no host sync)"""
+        L.check(self.lib.sw4b200_grid_record_resident(self.h, int(step)))
+
     def set_stream(self, st):
         L.check(self.lib.sw4b200_grid_set_stream(self.h, int(st)))
 

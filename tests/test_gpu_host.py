@@ -70,7 +70,7 @@ def timing_summary(out):
 
 
 @needs_exe
-@pytest.mark.parametrize("name,npts,nsteps", [("LOH.1-h100", 301 * 301 * 171, 536), ("LOH.1-h50", 601 * 601 * 341, 1072)])
+@pytest.mark.parametrize("name,npts,nsteps", [("LOH.1-h100", 301 * 301 * 171, 536), ("LOH.1-h50", 601 * 601 * 341, 1073)])
 def test_reference_program_loh1_station(tmp_path, name, npts, nsteps):
     """config 3: tests/loh1/LOH.1-h{100,50}.in through the reference's own main() on the grid-block kernels (odd ni: rows
     padded on the device, TMA kernels); the station file the reference's TimeSeries writes must match the reference's golden

@@ -68,3 +68,32 @@ def test_slabs_tile_the_grid(nz, n):
         assert b[0] == a[1] + 1
     sizes = [b - a + 1 for a, b in owned]
     assert max(sizes) - min(sizes) <= 5      # decomp1d balances the padded blocks; the end slabs own up to 2+2 more planes
+
+
+@needs_ref
+def test_loh1_problem_equals_the_references_setup(tmp_path):
+    """BASELINE.json config 3 at h=100: CartesianProblem.loh1 + tests/golden/loh1-h100-setup.npz against the reference's parser,
+    set-up and source discretisation for tests/loh1/LOH.1-h100.in"""
+    from tests.test_gpu_step import SourceMap
+    here = os.path.dirname(os.path.abspath(__file__))
+    ew = refshim.RefEW(os.path.join(here, "golden", "inputs", "LOH.1-h100.in"), str(tmp_path))
+    prob = CartesianProblem.loh1(100.0)
+    fx = np.load(os.path.join(here, "golden", "loh1-h100-setup.npz"))
+    G = ew.grids[0]
+    assert G.bounds == prob.bounds and list(G.bctype) == list(prob.bctype) and np.array_equal(G.wind, prob.wind)
+    assert prob.nsteps == ew.nsteps == int(fx["nsteps"]) and abs(prob.dt - ew.dt) <= 1e-16 and float(fx["dt"]) == ew.dt
+    for name, mine in (("mu", prob.mu), ("lambda", prob.la), ("rho", prob.rho)):
+        ref = np.array(ew.array(name, 0))
+        assert np.max(np.abs(ref - mine)) <= 1e-15 * np.max(np.abs(ref)), name
+    for name in ("strx", "stry", "strz", "dcx", "dcy", "dcz", "cox", "coy", "coz"):
+        assert np.max(np.abs(np.array(ew.array(name, 0)) - getattr(prob, name))) <= 4e-16, name
+    assert abs(ew.beta - prob.beta) < 1e-16
+    src = SourceMap(ew)
+    assert np.array_equal(src.points, fx["ijk"])
+    for s in (0, 17, 21, 40, 300):
+        t = ew.tstart + s * ew.dt
+        f = src.reduce(ew.eval_forces(t, False)); ftt = src.reduce(ew.eval_forces(t, True))
+        assert np.abs(f - fx["F0"] * fx["g"][s]).max() <= 1e-14 * max(np.abs(f).max(), 1e-300)
+        assert np.abs(ftt - fx["F0"] * fx["gtt"][s]).max() <= 1e-14 * max(np.abs(ftt).max(), 1e-300)
+    recs, _ = ew.receivers()
+    assert np.array_equal(np.array(recs)[:, 1:4], fx["rec"])
