@@ -3,7 +3,12 @@
 the Cartesian grid of pytest/reference/topo/curvilinear.in is z-slab decomposed over the ranks, the curvilinear
 grid under the topography lives on rank 0 and is coupled through EW::enforceCartTopo; the result must equal
 the single-GPU GridStack run bit for bit.  The set-up arrays come from the reference's own set-up (oracle/_ref),
-which is test infrastructure.   torchrun --nproc-per-node N scripts/check_topo_multigpu.py [nsteps]"""
+which is test infrastructure.
+   torchrun --nproc-per-node N scripts/check_topo_multigpu.py [nsteps] [input.in] [balance]
+input.in: a file of tests/golden/inputs (default curvilinear.in; gaussianHill-rev.in = BASELINE.json config 4, 128 x 128 x 1900
+Cartesian + 128 x 128 x 106 curvilinear points).  balance = 1: the rank holding the curvilinear grid owns fewer Cartesian planes
+(a curvilinear point costs about three Cartesian ones).  Prints the device time per step of the slab run (max over
+ranks) and of the single-GPU run next to the bit-identity verdict."""
 import os
 import sys
 import tempfile
@@ -48,15 +53,35 @@ def block(ew, g, device, curv=False, krange=None, halo=(False, False)):
     return blk
 
 
+def weighted_ranges(nz, world, ncurv_planes, weight=3.0, kmin=8):
+    """owned Cartesian planes per rank when rank 0 also steps `ncurv_planes` curvilinear planes costing `weight` each"""
+    if world == 1:
+        return [(1, nz)]
+    share = (nz + weight * ncurv_planes) / world
+    n0 = int(max(kmin, round(share - weight * ncurv_planes)))
+    rest = nz - n0
+    out = [(1, n0)]
+    k = n0 + 1
+    for r in range(1, world):
+        n = rest // (world - 1) + (1 if r - 1 < rest % (world - 1) else 0)
+        out.append((k, k + n - 1))
+        k += n
+    assert out[-1][1] == nz
+    return out
+
+
 def main():
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nsteps = int(sys.argv[1]) if len(sys.argv) > 1 else 12
+    infile = sys.argv[2] if len(sys.argv) > 2 else "curvilinear.in"
+    balance = len(sys.argv) > 3 and sys.argv[3] == "1"
     L.init(local); L.comm_init(rank, world)
+    lib = L.load()
     tmp = tempfile.mkdtemp()
     saved = os.dup(1); os.dup2(2, 1)          # the reference prints its set-up log
-    ew = refshim.RefEW(os.path.join(ROOT, "tests", "golden", "inputs", "curvilinear.in"), tmp)
+    ew = refshim.RefEW(os.path.join(ROOT, "tests", "golden", "inputs", infile), tmp)
     sys.stdout.flush(); os.dup2(saved, 1)
     assert ew.topo == 1 and ew.ngrids == 2
     srcs = [SourceMap(ew, g) for g in range(2)]
@@ -67,7 +92,10 @@ def main():
             b.set_source_points(srcs[g].points)
     # slab run
     G0 = ew.grids[0]
-    k0, k1 = slab_range(G0.nz, rank, world)
+    if balance:
+        k0, k1 = weighted_ranges(G0.nz, world, ew.grids[1].nz)[rank]
+    else:
+        k0, k1 = slab_range(G0.nz, rank, world)
     cart = block(ew, 0, local, krange=(k0, k1), halo=(rank > 0, rank < world - 1))
     sel = [n for n, pt in enumerate(srcs[0].points) if k0 <= pt[2] <= k1]
     if sel:
@@ -91,13 +119,33 @@ def main():
             cart.upload("Um", np.ascontiguousarray(um0.reshape(3, G.nk, nij)[:, c0:c0 + cart.nk]).ravel())
         elif curv is not None:
             curv.upload("U", u0); curv.upload("Um", um0)
-    t = ew.tstart
-    for s in range(nsteps):
+    times = [ew.tstart + s * ew.dt for s in range(nsteps)]
+    forces = []
+    for t in times:
         fa = ew.eval_forces(t, False); fta = ew.eval_forces(t, True)
-        f = [m.reduce(fa) for m in srcs]; ftt = [m.reduce(fta) for m in srcs]
-        stack.step(f, ftt)
-        stepper.step(f[0][sel] if sel else None, ftt[0][sel] if sel else None, f[1] if curv else None, ftt[1] if curv else None)
-        t += ew.dt
+        forces.append(([m.reduce(fa) for m in srcs], [m.reduce(fta) for m in srcs]))
+    import ctypes as C
+
+    def timed(fn):
+        L.check(lib.sw4b200_sync_device()); dist.barrier(); L.check(lib.sw4b200_sync_device())
+        L.check(lib.sw4b200_timer_start())
+        fn()
+        ms = C.c_double(0)
+        L.check(lib.sw4b200_timer_stop_ms(C.byref(ms)))
+        t = torch.tensor([ms.value], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def run_stack():
+        for f, ftt in forces:
+            stack.step(f, ftt)
+
+    def run_slabs():
+        for f, ftt in forces:
+            stepper.step(f[0][sel] if sel else None, ftt[0][sel] if sel else None, f[1] if curv else None, ftt[1] if curv else None)
+
+    ms_stack = timed(run_stack)
+    ms_slabs = timed(run_slabs)
     cart.sync()
     ref = stack.blocks[0].download("U").reshape(3, G0.nk, nij)[:, k0 - G0.bounds[4]:k1 - G0.bounds[4] + 1]
     mine = cart.download("U").reshape(3, cart.nk, nij)[:, 2:-2]
@@ -109,6 +157,12 @@ def main():
         same = same and sc
         msg += "; curvilinear grid: %s (scale %.3g)" % ("bit-identical" if sc else "DIFFERENT max|diff| %.3g" % np.abs(a - b).max(), np.abs(b).max())
     print(msg, flush=True)
+    if rank == 0:
+        pts = sum(G.nx * G.ny * G.nz for G in ew.grids)
+        print("TIMING %s: %d grid points (Cartesian %dx%dx%d + curvilinear %dx%dx%d), %d steps; z-slabs over %d GPU(s)%s: %.3f ms/step = %.3f Gpts/s; "
+              "single GPU (all ranks run it side by side): %.3f ms/step = %.3f Gpts/s" % (
+                  infile, pts, G0.nx, G0.ny, G0.nz, ew.grids[1].nx, ew.grids[1].ny, ew.grids[1].nz, nsteps, world,
+                  " (balanced)" if balance else "", ms_slabs / nsteps, pts * nsteps / ms_slabs / 1e6, ms_stack / nsteps, pts * nsteps / ms_stack / 1e6), flush=True)
     ok = torch.tensor([1 if same else 0], device="cuda")
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()

@@ -168,3 +168,23 @@ def test_cxx_slab_driver_matches_the_python_driver():
     ss, mx = float((own ** 2).sum()), float(np.abs(own).max())
     print("C++ slab driver vs Python: sum_sq %.15g / %.15g, max %.15g / %.15g" % (out["checksum"]["sum_sq"], ss, out["checksum"]["max_abs"], mx))
     assert mx > 0 and abs(out["checksum"]["max_abs"] - mx) <= 1e-9 * mx and abs(out["checksum"]["sum_sq"] - ss) <= 1e-9 * ss
+
+
+@needs_exe
+def test_reference_program_gaussian_hill_station(tmp_path):
+    """config 4: tests/topo/gaussianHill-rev.in (128 x 128 x 1900 Cartesian + 128 x 128 x 106 curvilinear points under a Gaussian
+    hill, 100 steps) through the reference's own main() on this repository's kernels; station sta04 against the reference's golden
+    file (tests/topo/gaussianHill-sta-04/sta04.txt)"""
+    out = run("gaussianHill-rev.in", str(tmp_path))
+    f = [p for p in tmp_path.rglob("sta04.txt")]
+    assert f, out[-2000:]
+    mine = station(str(f[0]))
+    gold = station(os.path.join(HERE, "golden", "gaussianHill-sta-04", "sta04.txt"))
+    n = min(len(mine), len(gold))
+    assert n >= 101
+    scale = np.abs(gold[:n, 1:4]).max()
+    err = np.abs(mine[:n, 1:4] - gold[:n, 1:4]).max() / scale
+    cols = timing_summary(out)
+    print("gaussianHill-rev through the C++ host: sta04 rel. diff %.3g over %d samples (amplitude %.3g); solver %.3f s for 99 steps = %.2f Gpts/s"
+          % (err, n, scale, cols[0], (128 * 128 * 1900 + 128 * 128 * 106) * 99 / cols[0] / 1e9))
+    assert scale > 0 and err < 1e-9
