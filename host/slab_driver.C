@@ -198,8 +198,7 @@ int main( int argc, char** argv )
    if( world > 1 ) B200( sw4b200_grid_set_neighbours( G, halo_lo ? rank - 1 : -1, halo_hi ? rank + 1 : -1 ) );
 
    // ---- sources: a 6 x 6 x 6 cloud of point forces (one moment-tensor source, GridPointSource.C), owned by the slab holding them
-   const int nzl_eff = nz / world;
-   const int ci = nx / 2, cj = ny / 2, ck = std::max( 8, std::min( nzl_eff / 2, nz - 8 ) );
+   const int ci = nx / 2, cj = ny / 2, ck = std::max( 8, std::min( 32, nz - 8 ) ); // (the same point whatever the number of slabs)
    std::vector<int> ijk;
    std::vector<double> amp;
    unsigned long long lcg = 12345;

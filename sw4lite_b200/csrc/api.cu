@@ -260,6 +260,7 @@ struct sw4b200_grid
    double *U, *Um, *Up, *Uacc; // Uacc: stored acceleration (SoA fast path) / second Up buffer (general path)
    double *mu, *la, *rho, *jac, *met;
    double* Lu;		       // curvilinear blocks: L(u) scratch of the unfused sequence
+   double* flux;	       // curvilinear blocks: the 9 flux arrays of the two-sweep operator (curvilinear.cu)
    bool fast;		       // SoA Cartesian throughput path
    std::vector<double>* h_dc[3]; // host copies of the damping arrays -> boxes where the damping is non-zero
    std::vector<Int6>* sgd_boxes;
@@ -543,8 +544,10 @@ int sw4b200_rhs4sgcurv( int corder, int ifirst, int ilast, int jfirst, int jlast
 			double* lu, const int* onesided, const double* strx, const double* stry, void* stream )
 {
    if( need_init() || check_bounds( ifirst, ilast, jfirst, jlast, kfirst, klast ) ) return 1;
-   return launch_rhs4sgcurv( make_block( corder, ifirst, ilast, jfirst, jlast, kfirst, klast ), u, mu, la, met, jac,
-			     lu, onesided[4] == 1, strx, stry, as_stream( stream ) );
+   const Block b = make_block( corder, ifirst, ilast, jfirst, jlast, kfirst, klast );
+   double* fl = scratch( as_stream( stream ), 9 * (size_t)b.npts ); // flux arrays of the two-sweep interior rows
+   if( !fl ) return 1;
+   return launch_rhs4sgcurv( b, u, mu, la, met, jac, lu, onesided[4] == 1, strx, stry, as_stream( stream ), fl );
 }
 int sw4b200_addsgdc( int corder, int order, int ifirst, int ilast, int jfirst, int jlast, int kfirst, int klast,
 		     double* up, const double* u, const double* um, const double* rho, const double* dcx,
@@ -701,6 +704,8 @@ static int grid_alloc( sw4b200_grid* g )
       if( !( g->jac = (double*)sw4b200_malloc( np * 8 ) ) ) return 1;
       if( !( g->met = (double*)sw4b200_malloc( 4 * np * 8 ) ) ) return 1;
       if( !( g->Lu = (double*)sw4b200_malloc( 3 * np * 8 ) ) ) return 1;
+      if( !( g->flux = (double*)sw4b200_malloc( 9 * np * 8 ) ) ) return 1;
+      cudaMemsetAsync( g->flux, 0, 9 * np * 8, g->st );
       cudaMemsetAsync( g->jac, 0, np * 8, g->st );
       cudaMemsetAsync( g->met, 0, 4 * np * 8, g->st );
       cudaMemsetAsync( g->Lu, 0, 3 * np * 8, g->st );
@@ -795,7 +800,7 @@ int sw4b200_grid_destroy( sw4b200_grid* g )
    if( !g ) return 0;
    cudaStreamSynchronize( g->st );
    double* ptrs[] = { g->U, g->Um, g->Up, g->Uacc, g->mu, g->la, g->rho, g->jac, g->met, g->d_f, g->d_rec,
-		      g->d_fser, g->d_fttser, g->d_recser, g->Lu };
+		      g->d_fser, g->d_fttser, g->d_recser, g->Lu, g->flux };
    for( int d = 0; d < 3; d++ ) delete g->h_dc[d];
    delete g->sgd_boxes;
    delete g->sgd_zonly;
@@ -1153,7 +1158,7 @@ int sw4b200_grid_corrector( sw4b200_grid* g, const double* h_ftt )
 static int curv_predictor_dev( sw4b200_grid* g, const double* d_f )
 {
    const double dt2 = g->d.dt * g->d.dt;
-   if( launch_rhs4sgcurv( g->b, g->U, g->mu, g->la, g->met, g->jac, g->Lu, g->d.onesided[4] == 1, g->str[0], g->str[1], g->st ) )
+   if( launch_rhs4sgcurv( g->b, g->U, g->mu, g->la, g->met, g->jac, g->Lu, g->d.onesided[4] == 1, g->str[0], g->str[1], g->st, g->flux ) )
       return 1;
    if( launch_predfort( g->b, g->Up, g->U, g->Um, g->Lu, 0, g->rho, dt2, g->st ) ) return 1;
    return d_f ? inject_dev( g, d_f, dt2, false, 0 ) : 0;
@@ -1162,7 +1167,7 @@ static int curv_corrector_dev( sw4b200_grid* g, const double* d_ftt )
 {
    const double dt2 = g->d.dt * g->d.dt;
    if( launch_dpdmt( 3 * g->b.npts, g->Up, g->U, g->Um, g->Uacc, 1.0 / dt2, g->st ) ) return 1;
-   if( launch_rhs4sgcurv( g->b, g->Uacc, g->mu, g->la, g->met, g->jac, g->Lu, g->d.onesided[4] == 1, g->str[0], g->str[1], g->st ) )
+   if( launch_rhs4sgcurv( g->b, g->Uacc, g->mu, g->la, g->met, g->jac, g->Lu, g->d.onesided[4] == 1, g->str[0], g->str[1], g->st, g->flux ) )
       return 1;
    if( launch_corrfort( g->b, g->Up, g->Lu, 0, g->rho, dt2 * dt2, g->st ) ) return 1;
    if( d_ftt && inject_dev( g, d_ftt, dt2 * dt2 / 12, false, 0 ) ) return 1;

@@ -130,7 +130,7 @@ int launch_halo_copy( const Block& b, double* field, int kplane, double* buf, in
 // curvilinear (curvilinear.cu)
 int launch_rhs4sgcurv( const Block& b, const double* u, const double* mu, const double* la, const double* met,
 		       const double* jac, double* lu, int onesided4, const double* strx, const double* stry,
-		       cudaStream_t st );
+		       cudaStream_t st, double* flux_scratch = 0 ); // flux_scratch: 9*npts doubles (two-sweep interior rows) or null
 int launch_addsgdc( int order, const Block& b, double* up, const double* u, const double* um, const double* rho,
 		    const double* dcx, const double* dcy, const double* strx, const double* stry,
 		    const double* jac, const double* cox, const double* coy, double beta, cudaStream_t st );

@@ -259,6 +259,164 @@ __global__ void __launch_bounds__( 128 ) k_rhs4sgcurv( CurvArgs a, int k_lo, int
    for( int c = 0; c < 3; c++ ) a.lu[c * b.sc + b.sp * p] = r[c];
 }
 
+// ---- interior rows in two sweeps with shared fluxes (no point evaluates another point's first differences).
+// With  X_c = sum_{b != p, d} N^{pb}_{cd} D_b u_d  (the part of the p-flux that is differenced by the centred D_p), and Y, Z
+// likewise for q and r, the operator is
+//    J L_c = sx [ G_p(N^{pp}) u + D0_p X ]_c + sy [ G_q(N^{qq}) u + D0_q Y ]_c + [ G_r(N^{rr}) u + D0_r Z ]_c .
+// k_curv_flux evaluates X, Y, Z once per point (9 first differences of u,v,w and the metric products) into scratch arrays;
+// k_curv_apply adds the three variable-coefficient second differences and the centred differences of the stored fluxes and
+// finishes with the Jacobian.  The one-thread-per-point kernel above re-evaluates the fluxes of its 12 neighbours
+// (about 1100 fp64 instructions per point); the two sweeps need about 600, for 72 B per point of scratch traffic each way.
+// The free-surface closure rows k=1..6 keep the kernel above.
+struct CurvFlux
+{
+   double* x[3]; // X_c, Y_c, Z_c: one value per grid point (point-indexed, whatever the layout of u)
+   double* y[3];
+   double* z[3];
+};
+
+__global__ void __launch_bounds__( 128 ) k_curv_flux( CurvArgs a, CurvFlux f, int k_lo, int k_hi )
+{
+   const Block& b = a.b;
+   const int li = blockIdx.x * blockDim.x + threadIdx.x;
+   const int lj = blockIdx.y * blockDim.y + threadIdx.y;
+   const int k = k_lo - 2 + blockIdx.z * blockDim.z + threadIdx.z; // planes k_lo-2 .. k_hi+2 (Z is differenced in r)
+   if( li > b.nil - 1 || lj > b.nj - 1 || k > k_hi + 2 ) return;
+   const int lk = k - b.kfirst;
+   if( lk < 0 || lk > b.nk - 1 ) return;
+   const long long sc = b.sc, sp = b.sp, dj = b.ni, dk = b.nij;
+   const long long p = (long long)li + dj * lj + dk * lk;
+   const double c1 = 2.0 / 3, c2 = -1.0 / 12;
+   auto U = [&]( int c, long long q ) { return a.u[c * sc + sp * q]; };
+   auto d0 = [&]( int c, long long st ) {
+      return c2 * ( U( c, p + 2 * st ) - U( c, p - 2 * st ) ) + c1 * ( U( c, p + st ) - U( c, p - st ) );
+   };
+   const bool iin = li >= 2 && li <= b.nil - 3, jin = lj >= 2 && lj <= b.nj - 3, kin = lk >= 2 && lk <= b.nk - 3 && k >= k_lo && k <= k_hi;
+   const double M = a.mu[p], L = a.la[p], l2m = 2 * M + L;
+   const double m1 = a.met[0 * a.msc + a.msp * p], m2 = a.met[1 * a.msc + a.msp * p], m3 = a.met[2 * a.msc + a.msp * p],
+		m4 = a.met[3 * a.msc + a.msp * p];
+   const double sx = a.strx[li], sy = a.stry[lj];
+   double dp[3] = { 0, 0, 0 }, dq[3] = { 0, 0, 0 }, dr[3] = { 0, 0, 0 };
+   if( iin )
+   {
+#pragma unroll
+      for( int c = 0; c < 3; c++ ) dp[c] = d0( c, 1 );
+   }
+   if( jin )
+   {
+#pragma unroll
+      for( int c = 0; c < 3; c++ ) dq[c] = d0( c, dj );
+   }
+   if( kin )
+   {
+#pragma unroll
+      for( int c = 0; c < 3; c++ ) dr[c] = d0( c, dk );
+   }
+   if( jin && kin ) // X: differenced in p by the points (i +- 1,2, j, k)
+   {
+      const double m12s = m1 * m2 * sx, m13y = m1 * m3 * sy, m11y = m1 * m1 * sy, m14 = m1 * m4;
+      f.x[0][p] = L * m11y * dq[1] + l2m * m12s * dr[0] + L * m13y * dr[1] + L * m14 * dr[2];
+      f.x[1][p] = M * m11y * dq[0] + M * m13y * dr[0] + M * m12s * dr[1];
+      f.x[2][p] = M * m14 * dr[0] + M * m12s * dr[2];
+   }
+   if( iin && kin ) // Y: differenced in q
+   {
+      const double m13s = m1 * m3 * sy, m12x = m1 * m2 * sx, m11x = m1 * m1 * sx, m14 = m1 * m4;
+      f.y[0][p] = M * m11x * dp[1] + M * m13s * dr[0] + M * m12x * dr[1];
+      f.y[1][p] = L * m11x * dp[0] + L * m12x * dr[0] + l2m * m13s * dr[1] + L * m14 * dr[2];
+      f.y[2][p] = M * m14 * dr[1] + M * m13s * dr[2];
+   }
+   if( iin && jin ) // Z: differenced in r (in-plane differences only: defined on the ghost planes too)
+   {
+      const double a1 = m2 * sx, a2 = m3 * sy, a3 = m4, e = m1 * sx, g = m1 * sy;
+      f.z[0][p] = l2m * a1 * e * dp[0] + M * a2 * e * dp[1] + M * a3 * e * dp[2] + M * a2 * g * dq[0] + L * a1 * g * dq[1];
+      f.z[1][p] = L * a2 * e * dp[0] + M * a1 * e * dp[1] + M * a1 * g * dq[0] + l2m * a2 * g * dq[1] + M * a3 * g * dq[2];
+      f.z[2][p] = L * a3 * e * dp[0] + M * a1 * e * dp[2] + L * a3 * g * dq[1] + M * a2 * g * dq[2];
+   }
+}
+
+__global__ void __launch_bounds__( 128 ) k_curv_apply( CurvArgs a, CurvFlux f, int k_lo, int k_hi )
+{
+   const Block& b = a.b;
+   const int li = 2 + blockIdx.x * blockDim.x + threadIdx.x;
+   const int lj = 2 + blockIdx.y * blockDim.y + threadIdx.y;
+   const int k = k_lo + blockIdx.z * blockDim.z + threadIdx.z;
+   if( li > b.nil - 3 || lj > b.nj - 3 || k > k_hi ) return;
+   const int lk = k - b.kfirst;
+   const long long sc = b.sc, sp = b.sp, dj = b.ni, dk = b.nij;
+   const long long p = (long long)li + dj * lj + dk * lk;
+   const double c1 = 2.0 / 3, c2 = -1.0 / 12, i6 = 1.0 / 6;
+   auto U = [&]( int c, long long q ) { return a.u[c * sc + sp * q]; };
+   auto MET = [&]( int c, long long q ) { return a.met[c * a.msc + a.msp * q]; };
+   const double sxi = a.strx[li], syj = a.stry[lj];
+   const double u0[3] = { U( 0, p ), U( 1, p ), U( 2, p ) };
+   double r[3];
+   // ---- p and q: G(mu m1^2 s) on two components, G((2mu+la) m1^2 s) on the own one, plus the centred difference of the flux
+   auto inplane = [&]( long long st, const double* str, int own, double* const* flux, double out[3] ) {
+      double cm[5], cl[5], wm[4], wl[4];
+#pragma unroll
+      for( int m = -2; m <= 2; m++ )
+      {
+	 const long long q = p + m * st;
+	 const double M = a.mu[q], L = a.la[q], m1 = MET( 0, q );
+	 const double t = m1 * m1 * str[m];
+	 cm[m + 2] = M * t;
+	 cl[m + 2] = ( 2 * M + L ) * t;
+      }
+      cweights4( cl, wl );
+      cweights4( cm, wm );
+#pragma unroll
+      for( int c = 0; c < 3; c++ )
+      {
+	 const double* w = c == own ? wl : wm;
+	 const double g = w[0] * ( U( c, p - 2 * st ) - u0[c] ) + w[1] * ( U( c, p - st ) - u0[c] ) + w[2] * ( U( c, p + st ) - u0[c] ) +
+			  w[3] * ( U( c, p + 2 * st ) - u0[c] );
+	 out[c] = i6 * g + ( c2 * ( flux[c][p + 2 * st] - flux[c][p - 2 * st] ) + c1 * ( flux[c][p + st] - flux[c][p - st] ) );
+      }
+   };
+   double rp[3], rq[3];
+   inplane( 1, a.strx + li, 0, f.x, rp );
+   inplane( dj, a.stry + lj, 1, f.y, rq );
+   // ---- r: the full coefficient matrix N^{rr} = la A A^T + mu (|A|^2 I + A A^T), A = (m2 sx, m3 sy, m4)
+   {
+      double n11[5], n22[5], n33[5], n12[5], n13[5], n23[5];
+#pragma unroll
+      for( int m = -2; m <= 2; m++ )
+      {
+	 const long long q = p + m * dk;
+	 const double M = a.mu[q], L = a.la[q];
+	 const double a1 = MET( 1, q ) * sxi, a2 = MET( 2, q ) * syj, a3 = MET( 3, q );
+	 const double l2m = 2 * M + L, lm = M + L;
+	 n11[m + 2] = l2m * a1 * a1 + M * ( a2 * a2 + a3 * a3 );
+	 n22[m + 2] = l2m * a2 * a2 + M * ( a1 * a1 + a3 * a3 );
+	 n33[m + 2] = l2m * a3 * a3 + M * ( a1 * a1 + a2 * a2 );
+	 n12[m + 2] = lm * a1 * a2;
+	 n13[m + 2] = lm * a1 * a3;
+	 n23[m + 2] = lm * a2 * a3;
+      }
+      double w11[4], w22[4], w33[4], w12[4], w13[4], w23[4];
+      cweights4( n11, w11 ); cweights4( n22, w22 ); cweights4( n33, w33 );
+      cweights4( n12, w12 ); cweights4( n13, w13 ); cweights4( n23, w23 );
+      double du[3][4];
+#pragma unroll
+      for( int c = 0; c < 3; c++ )
+      {
+	 du[c][0] = U( c, p - 2 * dk ) - u0[c]; du[c][1] = U( c, p - dk ) - u0[c];
+	 du[c][2] = U( c, p + dk ) - u0[c]; du[c][3] = U( c, p + 2 * dk ) - u0[c];
+      }
+      auto g = [&]( const double w[4], int d ) { return w[0] * du[d][0] + w[1] * du[d][1] + w[2] * du[d][2] + w[3] * du[d][3]; };
+      r[0] = i6 * ( g( w11, 0 ) + g( w12, 1 ) + g( w13, 2 ) );
+      r[1] = i6 * ( g( w12, 0 ) + g( w22, 1 ) + g( w23, 2 ) );
+      r[2] = i6 * ( g( w13, 0 ) + g( w23, 1 ) + g( w33, 2 ) );
+#pragma unroll
+      for( int c = 0; c < 3; c++ )
+	 r[c] += c2 * ( f.z[c][p + 2 * dk] - f.z[c][p - 2 * dk] ) + c1 * ( f.z[c][p + dk] - f.z[c][p - dk] );
+   }
+   const double ij = 1.0 / a.jac[p];
+#pragma unroll
+   for( int c = 0; c < 3; c++ ) a.lu[c * sc + sp * p] = ( sxi * rp[c] + syj * rq[c] + r[c] ) * ij;
+}
+
 // supergrid damping on the curvilinear grid: x and y terms only, weights rho*dc*jac, prefactor beta/(rho*jac)
 __device__ __forceinline__ double sgdc_dir( int order, const double* __restrict__ u, const double* __restrict__ um,
 					    const double* __restrict__ rho, const double* __restrict__ jac,
@@ -397,7 +555,7 @@ static void curv_args( CurvArgs& a, const Block& b, const double* u, const doubl
 
 int launch_rhs4sgcurv( const Block& b, const double* u, const double* mu, const double* la, const double* met,
 		       const double* jac, double* lu, int onesided4, const double* strx, const double* stry,
-		       cudaStream_t st )
+		       cudaStream_t st, double* flux_scratch )
 {
    if( b.nil < 5 || b.nj < 5 || b.nk < 5 ) return 0;
    CurvArgs a;
@@ -415,7 +573,23 @@ int launch_rhs4sgcurv( const Block& b, const double* u, const double* mu, const 
       count_launch();
       kstart = 7;
    }
-   if( kend >= kstart )
+   if( kend >= kstart && flux_scratch )
+   {
+      // interior rows in two sweeps: fluxes once per point (9 * npts doubles of scratch), then the operator
+      CurvFlux f;
+      for( int c = 0; c < 3; c++ )
+      {
+	 f.x[c] = flux_scratch + (size_t)c * b.npts;
+	 f.y[c] = flux_scratch + (size_t)( 3 + c ) * b.npts;
+	 f.z[c] = flux_scratch + (size_t)( 6 + c ) * b.npts;
+      }
+      dim3 gf( ( b.nil + bs.x - 1 ) / bs.x, ( b.nj + bs.y - 1 ) / bs.y, kend - kstart + 5 );
+      k_curv_flux<<<gf, bs, 0, st>>>( a, f, kstart, kend );
+      dim3 gs( ( b.nil - 4 + bs.x - 1 ) / bs.x, ( b.nj - 4 + bs.y - 1 ) / bs.y, kend - kstart + 1 );
+      k_curv_apply<<<gs, bs, 0, st>>>( a, f, kstart, kend );
+      count_launch( 2 );
+   }
+   else if( kend >= kstart )
    {
       dim3 gs( ( b.nil - 4 + bs.x - 1 ) / bs.x, ( b.nj - 4 + bs.y - 1 ) / bs.y, kend - kstart + 1 );
       k_rhs4sgcurv<false><<<gs, bs, 0, st>>>( a, kstart, kend );
