@@ -172,19 +172,48 @@ def test_cxx_slab_driver_matches_the_python_driver():
 
 @needs_exe
 def test_reference_program_gaussian_hill_station(tmp_path):
-    """config 4: tests/topo/gaussianHill-rev.in (128 x 128 x 1900 Cartesian + 128 x 128 x 106 curvilinear points under a Gaussian
-    hill, 100 steps) through the reference's own main() on this repository's kernels; station sta04 against the reference's golden
-    file (tests/topo/gaussianHill-sta-04/sta04.txt)"""
-    out = run("gaussianHill-rev.in", str(tmp_path))
+    """config 4: tests/topo/gaussianHill.in (Gaussian hill topography: 101 x 101 x 51 Cartesian + 101 x 101 x 110 curvilinear points,
+    corder=no, 789 steps to t=3) through the reference's own main() on this repository's kernels; station sta04 against the
+    reference's golden file (tests/topo/gaussianHill-sta-04/sta04.txt)"""
+    out = run("gaussianHill.in", str(tmp_path))
     f = [p for p in tmp_path.rglob("sta04.txt")]
     assert f, out[-2000:]
     mine = station(str(f[0]))
     gold = station(os.path.join(HERE, "golden", "gaussianHill-sta-04", "sta04.txt"))
-    n = min(len(mine), len(gold))
-    assert n >= 101
-    scale = np.abs(gold[:n, 1:4]).max()
-    err = np.abs(mine[:n, 1:4] - gold[:n, 1:4]).max() / scale
-    cols = timing_summary(out)
-    print("gaussianHill-rev through the C++ host: sta04 rel. diff %.3g over %d samples (amplitude %.3g); solver %.3f s for 99 steps = %.2f Gpts/s"
-          % (err, n, scale, cols[0], (128 * 128 * 1900 + 128 * 128 * 106) * 99 / cols[0] / 1e9))
+    assert mine.shape == gold.shape and len(gold) == 790
+    scale = np.abs(gold[:, 1:4]).max()
+    err = np.abs(mine[:, 1:4] - gold[:, 1:4]).max() / scale
+    print("gaussianHill through the C++ host: sta04 rel. diff %.3g over %d samples (amplitude %.3g)" % (err, len(gold), scale))
     assert scale > 0 and err < 1e-9
+
+
+REF_EXE = os.path.join(HERE, "..", "oracle", "_ref", "sw4lite_ref")
+
+
+@needs_exe
+@pytest.mark.skipif(not os.path.exists(REF_EXE), reason="oracle/_ref/sw4lite_ref not built")
+def test_reference_program_gaussian_hill_rev_against_the_cpu_reference(tmp_path):
+    """config 4 at its multi-rank size: tests/topo/gaussianHill-rev.in (128 x 128 x 1900 Cartesian + 128 x 128 x 106 curvilinear
+    points, corder=yes, 100 steps).  No golden file exists for it, so the unmodified CPU reference program (oracle/_ref) runs the
+    same input beside the GPU build; the four station files must agree"""
+    a, b = tmp_path / "gpu", tmp_path / "cpu"
+    a.mkdir(); b.mkdir()
+    out = run("gaussianHill-rev.in", str(a))
+    env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 8))
+    r = subprocess.run([REF_EXE, os.path.join(INPUTS, "gaussianHill-rev.in")], cwd=str(b), capture_output=True, text=True, timeout=1500, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    worst, amp = 0.0, 0.0
+    for name in ("sta01.txt", "sta02.txt", "sta03.txt", "sta04.txt"):
+        fa, fb = list(a.rglob(name)), list(b.rglob(name))
+        assert fa and fb, name
+        ma, mb = station(str(fa[0])), station(str(fb[0]))
+        assert ma.shape == mb.shape and len(mb) == 101
+        scale = np.abs(mb[:, 1:4]).max()
+        amp = max(amp, scale)
+        if scale > 0:
+            worst = max(worst, np.abs(ma[:, 1:4] - mb[:, 1:4]).max() / scale)
+    cols, cols_cpu = timing_summary(out), timing_summary(r.stdout)
+    pts = 128 * 128 * 1900 + 128 * 128 * 106
+    print("gaussianHill-rev: stations GPU vs CPU reference rel. diff %.3g (amplitude %.3g); solver GPU %.3f s = %.2f Gpts/s, CPU reference %.1f s = %.3f Gpts/s (%d threads)"
+          % (worst, amp, cols[0], pts * 99 / cols[0] / 1e9, cols_cpu[0], pts * 99 / cols_cpu[0] / 1e9, os.cpu_count() or 8))
+    assert amp > 0 and worst < 1e-9
