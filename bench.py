@@ -409,7 +409,7 @@ def main_ours(a):
     ms_e2e = timed(total, a.steps, True)
 
     prof = {}
-    for name in ("rhs_fast_pred", "rhs_fast_corr", "closure", "rhs_v1", "addsgd", "shell", "bc"):
+    for name in ("rhs_fast_pred", "rhs_fast_corr", "closure", "rhs_v1", "addsgd", "shell", "bc", "exchange_pred", "exchange_corr"):
         tot = C.c_double(0); cnt = C.c_longlong(0)
         lib.sw4b200_profile_read(name.encode(), C.byref(tot), C.byref(cnt))
         if cnt.value:

@@ -1301,6 +1301,7 @@ int sw4b200_grid_exchange_begin( sw4b200_grid* g, int with_acc )
    cudaStream_t cs = g_streams[3];
    CUDA_OK( cudaEventRecord( g->ev_face, g->st ) );
    CUDA_OK( cudaStreamWaitEvent( cs, g->ev_face, 0 ) );
+   ProfScope prof( with_acc ? "exchange_pred" : "exchange_corr", cs ); // (device time of the transfer on the communication stream)
    if( exchange_group_start() ) return 1;
    int rc = exchange_field( g->b, g->Up, g->peer_lo, g->peer_hi, cs );
    if( !rc && with_acc && g->fast ) rc = exchange_field( g->b, g->Uacc, g->peer_lo, g->peer_hi, cs );
