@@ -465,6 +465,9 @@ def main_ours(a):
                     "note": "per-step C-ABI (sw4b200_grid_step / _part): host source amplitudes in, host receiver samples out each "
                             "step; the wavefield stays device resident as in the reference's own time loop (EW.C:2455-2477)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": prof}
+    if N > 1:
+        line["config"]["exchange"] = {1: "peer-to-peer pushes by the copy engines (CUDA IPC over NVLink), flags for ordering",
+                                      0: "NCCL send/receive straight from the field arrays"}.get(lib.sw4b200_grid_exchange_transport(blk.h), "none")
     if N == 1 and not a.no_cpu_baseline:
         try:
             g, cms, threads, sample = time_reference(a.cpu_grid, 4, 1)

@@ -292,6 +292,10 @@ int sw4b200_comm_allreduce( double* h_values, int n, int op );
 int sw4b200_timer_start( void );
 int sw4b200_timer_stop_ms( double* ms );
 int sw4b200_grid_set_neighbours( sw4b200_grid* g, int rank_lo, int rank_hi );   /* -1: no neighbour on that face */
+/* transport chosen by sw4b200_grid_set_neighbours: 1 = the copy engines push the planes into the neighbour's arrays, mapped
+ * through CUDA IPC (no SM involved; needs peer access between the GPUs), 0 = NCCL send / receive, -1 = no neighbours.
+ * sw4b200_set_option( "exchange_p2p", 0 ) before set_neighbours forces NCCL. */
+int sw4b200_grid_exchange_transport( sw4b200_grid* g );
 int sw4b200_grid_exchange_begin( sw4b200_grid* g, int with_acc );              /* after the face rows (part 1)   */
 int sw4b200_grid_exchange_end( sw4b200_grid* g );                              /* before the boundary conditions  */
 

@@ -283,6 +283,7 @@ struct sw4b200_grid
    // z-slab neighbours (ranks of the communicator, -1: none) and the events that order the exchange against the compute stream
    int peer_lo, peer_hi;
    cudaEvent_t ev_face, ev_halo;
+   P2PLink p2p; // peer-to-peer transport (exchange.cu): the neighbours' arrays mapped through CUDA IPC
 };
 
 extern "C" {
@@ -816,6 +817,7 @@ int sw4b200_grid_destroy( sw4b200_grid* g )
    if( g->d_recidx ) cudaFree( g->d_recidx );
    if( g->h_f ) cudaFreeHost( g->h_f );
    if( g->h_rec ) cudaFreeHost( g->h_rec );
+   p2p_release( g->p2p );
    if( g->ev_face ) cudaEventDestroy( g->ev_face );
    if( g->ev_halo ) cudaEventDestroy( g->ev_halo );
    delete g;
@@ -1057,6 +1059,7 @@ static void build_sgd_boxes( sw4b200_grid* g )
 }
 
 static int g_opt_sgd_zonly = 1; // sw4b200_set_option( "sgd_zonly", . )
+static int g_opt_p2p = 1;	// sw4b200_set_option( "exchange_p2p", . ): 0 = always NCCL send/receive
 static int damping_dev( sw4b200_grid* g, int part )
 {
    if( g->d.sg_order == 0 || g->d.beta == 0 ) return 0;
@@ -1296,7 +1299,22 @@ int sw4b200_grid_set_neighbours( sw4b200_grid* g, int rank_lo, int rank_hi )
    g->peer_lo = rank_lo; g->peer_hi = rank_hi;
    if( !g->ev_face ) CUDA_OK( cudaEventCreateWithFlags( &g->ev_face, cudaEventDisableTiming ) );
    if( !g->ev_halo ) CUDA_OK( cudaEventCreateWithFlags( &g->ev_halo, cudaEventDisableTiming ) );
+   // transport: peer-to-peer pushes by the copy engines when every rank can map its neighbours (CUDA IPC over NVLink),
+   // else NCCL send / receive.  All ranks of the communicator call this (ranks without a neighbour take part in the vote).
+   p2p_release( g->p2p );
+   if( g_opt_p2p && comm_size() > 1 )
+   {
+      CUDA_OK( cudaStreamSynchronize( g->st ) );
+      double* mine[4] = { g->U, g->Um, g->Up, g->Uacc };
+      if( p2p_setup( g->p2p, mine, g->b, rank_lo, rank_hi, g_streams[3] ) ) return 1;
+   }
    return 0;
+}
+// 1: peer-to-peer pushes by the copy engines (CUDA IPC), 0: NCCL send / receive, -1: the block has no neighbours
+int sw4b200_grid_exchange_transport( sw4b200_grid* g )
+{
+   if( g->peer_lo < 0 && g->peer_hi < 0 ) return -1;
+   return g->p2p.on ? 1 : 0;
 }
 // start moving the face planes of Up (with_acc: and of the stored acceleration, after the predictor) to / from the
 // neighbours on the communication stream, once everything queued on the block's stream so far (the face rows) is done
@@ -1307,6 +1325,13 @@ int sw4b200_grid_exchange_begin( sw4b200_grid* g, int with_acc )
    CUDA_OK( cudaEventRecord( g->ev_face, g->st ) );
    CUDA_OK( cudaStreamWaitEvent( cs, g->ev_face, 0 ) );
    ProfScope prof( with_acc ? "exchange_pred" : "exchange_corr", cs ); // (device time of the transfer on the communication stream)
+   if( g->p2p.on )
+   {
+      if( p2p_open( g->p2p, cs ) ) return 1;
+      if( p2p_push_field( g->p2p, g->b, g->Up, cs ) ) return 1;
+      if( with_acc && g->fast && p2p_push_field( g->p2p, g->b, g->Uacc, cs ) ) return 1;
+      return p2p_signal( g->p2p, cs );
+   }
    if( exchange_group_start() ) return 1;
    int rc = exchange_field( g->b, g->Up, g->peer_lo, g->peer_hi, cs );
    if( !rc && with_acc && g->fast ) rc = exchange_field( g->b, g->Uacc, g->peer_lo, g->peer_hi, cs );
@@ -1318,6 +1343,7 @@ int sw4b200_grid_exchange_begin( sw4b200_grid* g, int with_acc )
 int sw4b200_grid_exchange_end( sw4b200_grid* g )
 {
    if( g->peer_lo < 0 && g->peer_hi < 0 ) return 0;
+   if( g->p2p.on ) return p2p_wait( g->p2p, g->st );
    CUDA_OK( cudaStreamWaitEvent( g->st, g->ev_halo, 0 ) );
    return 0;
 }
@@ -1430,6 +1456,7 @@ int sw4b200_measure_fp64_peak( double* tflops, double* fma_per_s )
 int sw4b200_set_option( const char* name, int value )
 {
    if( name && !strcmp( name, "sgd_zonly" ) ) { g_opt_sgd_zonly = value != 0; return 0; }
+   if( name && !strcmp( name, "exchange_p2p" ) ) { g_opt_p2p = value != 0; return 0; }
    return set_error( "set_option: unknown option '%s'", name ? name : "(null)" );
 }
 

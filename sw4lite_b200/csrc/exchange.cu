@@ -16,6 +16,7 @@
 #include <nccl.h> // types only
 #include <dlfcn.h>
 #include <cstdio>
+#include <cstdlib>
 
 namespace sw4b200 {
 namespace {
@@ -25,6 +26,7 @@ struct NcclApi
    void* h;
    decltype( &ncclGetUniqueId ) GetUniqueId;
    decltype( &ncclCommInitRank ) CommInitRank;
+   decltype( &ncclCommInitRankConfig ) CommInitRankConfig; // (optional)
    decltype( &ncclCommDestroy ) CommDestroy;
    decltype( &ncclSend ) Send;
    decltype( &ncclRecv ) Recv;
@@ -50,6 +52,7 @@ int nccl_load()
    if( !g_nccl.field ) return set_error( "NCCL: symbol %s not found", name );
    SW4_SYM( GetUniqueId, "ncclGetUniqueId" )
    SW4_SYM( CommInitRank, "ncclCommInitRank" )
+   g_nccl.CommInitRankConfig = (decltype( g_nccl.CommInitRankConfig ))dlsym( h, "ncclCommInitRankConfig" );
    SW4_SYM( CommDestroy, "ncclCommDestroy" )
    SW4_SYM( Send, "ncclSend" )
    SW4_SYM( Recv, "ncclRecv" )
@@ -89,7 +92,21 @@ int comm_init( int rank, int nranks, const void* id128 )
    if( nccl_load() ) return 1;
    ncclUniqueId id;
    memcpy( &id, id128, sizeof( id ) );
-   NCCL_OK( g_nccl.CommInitRank( &g_comm, nranks, id, rank ) );
+   // The transfer kernels share the SMs with the bulk rows of the slab, whose thread blocks fill a whole SM each: every
+   // block NCCL runs takes an SM away from them for the length of the transfer.  A face exchange is 0.2-0.4 GB per neighbour
+   // under >= 15 ms of bulk work, so a few blocks are enough (default 8; SW4B200_NCCL_MAX_CTAS overrides, 0 = NCCL's own
+   // choice, 32 on an NVSwitch box).
+   int max_ctas = 8;
+   if( const char* e = getenv( "SW4B200_NCCL_MAX_CTAS" ) ) max_ctas = atoi( e );
+   if( g_nccl.CommInitRankConfig && max_ctas > 0 )
+   {
+      ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+      cfg.maxCTAs = max_ctas;
+      cfg.minCTAs = 1;
+      NCCL_OK( g_nccl.CommInitRankConfig( &g_comm, nranks, id, rank, &cfg ) );
+   }
+   else
+      NCCL_OK( g_nccl.CommInitRank( &g_comm, nranks, id, rank ) );
    return 0;
 }
 
@@ -141,6 +158,179 @@ int exchange_field( const Block& b, double* field, int peer_lo, int peer_hi, cud
       }
    }
    return 0;
+}
+
+// ---- peer-to-peer transport: the copy engines move the face planes, no SM is involved --------------------------------
+// Every rank maps its neighbours' solution arrays into its own address space (CUDA IPC) and PUSHES its face planes straight
+// into their halo planes with cudaMemcpyAsync on the communication stream: NVLink copies by the DMA engines, which neither
+// wait for nor take away an SM from the bulk rows (the NCCL transfer runs thread blocks: it starts late and slows the stencil
+// kernel down, which matters most for thin slabs).  Two counters per direction order it, each written into the other
+// rank's memory by a one-thread kernel and awaited by a one-thread spinning kernel:
+//   ready[n]    receiver -> sender: "my face rows of phase n are done", i.e. nothing of mine reads the halo planes of the
+//               previous exchange any more (their last readers -- the stencil of the face rows, the ghost-shell update, the
+//               damping of the face rows -- all belong to the face-row part that precedes my own exchange n);
+//   arrived[n]  sender -> receiver, behind the copies: the halo planes of exchange n are complete; the receiver's compute
+//               stream waits for it before the boundary conditions.
+// This is the ordering a receive posted after the face rows gives the NCCL path.  The handles travel once, at set-up, over
+// the NCCL communicator.
+struct P2PInfo // what one rank tells a neighbour
+{
+   cudaIpcMemHandle_t mem[4]; // U, Um, Up, Uacc allocations (in creation order: pointer rotation keeps them in step on all ranks)
+   cudaIpcMemHandle_t flags;  // counters written by the neighbours: arrived[0,1] (by the low / high neighbour), ready[2,3]
+   long long nk, nij, npts;
+   int valid;
+};
+struct P2PLink
+{
+   bool on;
+   double* mine[4];
+   unsigned long long* flags; // my counters (device memory)
+   struct Peer { int rank; double* base[4]; unsigned long long* flags; long long nk; } peer[2];
+   unsigned long long posted;	  // exchanges started so far (every rank counts the same)
+};
+
+namespace {
+__global__ void k_set_flag( unsigned long long* flag, unsigned long long value )
+{
+   __threadfence_system();
+   *reinterpret_cast<volatile unsigned long long*>( flag ) = value;
+   __threadfence_system();
+}
+__global__ void k_wait_flag( const unsigned long long* flag, unsigned long long value )
+{
+   const volatile unsigned long long* f = flag;
+   while( *f < value ) __nanosleep( 200 );
+   __threadfence_system();
+}
+} // namespace
+
+// map the neighbours' arrays; returns 0 and sets l.on if the peer-to-peer transport is usable on every rank involved
+int p2p_setup( P2PLink& l, double* const mine[4], const Block& b, int peer_lo, int peer_hi, cudaStream_t st )
+{
+   l.on = false;
+   l.posted = 0;
+   l.flags = 0;
+   for( int s = 0; s < 2; s++ ) { l.peer[s].rank = s == 0 ? peer_lo : peer_hi; l.peer[s].flags = 0; for( int a = 0; a < 4; a++ ) l.peer[s].base[a] = 0; }
+   for( int a = 0; a < 4; a++ ) l.mine[a] = mine[a];
+   if( !g_comm ) return 0;
+   P2PInfo me;
+   memset( &me, 0, sizeof( me ) );
+   me.valid = 1;
+   if( cudaMalloc( (void**)&l.flags, 4 * sizeof( unsigned long long ) ) != cudaSuccess ) me.valid = 0;
+   else cudaMemset( l.flags, 0, 4 * sizeof( unsigned long long ) );
+   for( int a = 0; a < 4 && me.valid; a++ )
+      if( cudaIpcGetMemHandle( &me.mem[a], mine[a] ) != cudaSuccess ) me.valid = 0;
+   if( me.valid && cudaIpcGetMemHandle( &me.flags, l.flags ) != cudaSuccess ) me.valid = 0;
+   cudaGetLastError();
+   me.nk = b.nk; me.nij = b.nij; me.npts = b.npts;
+   // swap the records with both neighbours
+   char* dbuf = 0;
+   if( cudaMalloc( (void**)&dbuf, 3 * sizeof( P2PInfo ) ) != cudaSuccess ) return set_error( "p2p_setup: cudaMalloc failed" );
+   cudaMemcpyAsync( dbuf, &me, sizeof( me ), cudaMemcpyHostToDevice, st );
+   NCCL_OK( g_nccl.GroupStart() );
+   for( int s = 0; s < 2; s++ )
+      if( l.peer[s].rank >= 0 )
+      {
+	 NCCL_OK( g_nccl.Send( dbuf, sizeof( P2PInfo ), ncclChar, l.peer[s].rank, g_comm, st ) );
+	 NCCL_OK( g_nccl.Recv( dbuf + ( 1 + s ) * sizeof( P2PInfo ), sizeof( P2PInfo ), ncclChar, l.peer[s].rank, g_comm, st ) );
+      }
+   NCCL_OK( g_nccl.GroupEnd() );
+   P2PInfo other[2];
+   cudaMemcpyAsync( other, dbuf + sizeof( P2PInfo ), 2 * sizeof( P2PInfo ), cudaMemcpyDeviceToHost, st );
+   cudaStreamSynchronize( st );
+   cudaFree( dbuf );
+   bool ok_ = me.valid != 0;
+   for( int s = 0; s < 2 && ok_; s++ )
+   {
+      if( l.peer[s].rank < 0 ) continue;
+      const P2PInfo& o = other[s];
+      if( !o.valid || o.nij != b.nij ) { ok_ = false; break; }
+      l.peer[s].nk = o.nk;
+      for( int a = 0; a < 4 && ok_; a++ )
+	 if( cudaIpcOpenMemHandle( (void**)&l.peer[s].base[a], o.mem[a], cudaIpcMemLazyEnablePeerAccess ) != cudaSuccess ) ok_ = false;
+      if( ok_ && cudaIpcOpenMemHandle( (void**)&l.peer[s].flags, o.flags, cudaIpcMemLazyEnablePeerAccess ) != cudaSuccess ) ok_ = false;
+   }
+   cudaGetLastError();
+   // all ranks of the communicator must agree (a rank that cannot map its neighbour makes both fall back to NCCL)
+   double agree = ok_ ? 1.0 : 0.0;
+   if( comm_allreduce( &agree, 1, 2, st ) ) return 1;
+   l.on = agree > 0.5;
+   return 0;
+}
+
+void p2p_release( P2PLink& l )
+{
+   for( int s = 0; s < 2; s++ )
+   {
+      for( int a = 0; a < 4; a++ )
+	 if( l.peer[s].base[a] ) { cudaIpcCloseMemHandle( l.peer[s].base[a] ); l.peer[s].base[a] = 0; }
+      if( l.peer[s].flags ) { cudaIpcCloseMemHandle( l.peer[s].flags ); l.peer[s].flags = 0; }
+   }
+   if( l.flags ) { cudaFree( l.flags ); l.flags = 0; }
+   l.on = false;
+   cudaGetLastError();
+}
+
+// push the face planes of `field` (one of my four arrays) into the neighbours' halo planes
+int p2p_push_field( P2PLink& l, const Block& b, const double* field, cudaStream_t st )
+{
+   int id = -1;
+   for( int a = 0; a < 4; a++ )
+      if( l.mine[a] == field ) id = a;
+   if( id < 0 ) return set_error( "p2p exchange: the field is not one of the block's solution arrays" );
+   const long long nij = b.nij;
+   const int nrun = b.sp == 1 ? 3 : 1;
+   const size_t bytes = (size_t)( b.sp == 1 ? 2 : 6 ) * nij * sizeof( double );
+   const long long pl = b.sp == 1 ? nij : 3 * nij;
+   for( int side = 0; side < 2; side++ )
+   {
+      const P2PLink::Peer& p = l.peer[side];
+      if( p.rank < 0 ) continue;
+      // my low face -> the low neighbour's HIGH halo planes; my high face -> the high neighbour's LOW halo planes
+      const long long ksend = side == 0 ? 2 : b.nk - 4, krecv = side == 0 ? p.nk - 2 : 0;
+      const long long peer_npts = nij * p.nk;
+      for( int r = 0; r < nrun; r++ )
+      {
+	 const double* src = field + ( b.sp == 1 ? r * b.sc : 0 ) + pl * ksend;
+	 double* dst = p.base[id] + ( b.sp == 1 ? r * peer_npts : 0 ) + pl * krecv;
+	 if( cudaMemcpyAsync( dst, src, bytes, cudaMemcpyDefault, st ) != cudaSuccess )
+	    return set_error( "p2p exchange: cudaMemcpyAsync to the neighbour failed: %s", cudaGetErrorString( cudaGetLastError() ) );
+      }
+   }
+   return 0;
+}
+
+// start of exchange n on the communication stream (behind the event of my face rows): tell the neighbours that their
+// pushes may land, and wait for the same word from them
+int p2p_open( P2PLink& l, cudaStream_t st )
+{
+   l.posted++;
+   for( int side = 0; side < 2; side++ )
+      if( l.peer[side].rank >= 0 )
+	 k_set_flag<<<1, 1, 0, st>>>( l.peer[side].flags + 2 + ( side == 0 ? 1 : 0 ), l.posted ); // I am its high (low) neighbour
+   for( int side = 0; side < 2; side++ )
+      if( l.peer[side].rank >= 0 ) k_wait_flag<<<1, 1, 0, st>>>( l.flags + 2 + side, l.posted );
+   count_launch();
+   return check_launch( "k_set_flag / k_wait_flag" );
+}
+
+// behind the copies of one exchange: tell the neighbours that their halo planes are complete
+int p2p_signal( P2PLink& l, cudaStream_t st )
+{
+   for( int side = 0; side < 2; side++ )
+      if( l.peer[side].rank >= 0 )
+	 k_set_flag<<<1, 1, 0, st>>>( l.peer[side].flags + ( side == 0 ? 1 : 0 ), l.posted ); // I am its high (low) neighbour
+   count_launch();
+   return check_launch( "k_set_flag" );
+}
+
+// on the compute stream: wait until both neighbours have delivered the planes of the current exchange
+int p2p_wait( P2PLink& l, cudaStream_t st )
+{
+   for( int side = 0; side < 2; side++ )
+      if( l.peer[side].rank >= 0 ) k_wait_flag<<<1, 1, 0, st>>>( l.flags + side, l.posted );
+   count_launch();
+   return check_launch( "k_wait_flag" );
 }
 
 int exchange_group_start()

@@ -101,6 +101,7 @@ SIGNATURES = {
     "sw4b200_timer_start": (I, []),
     "sw4b200_timer_stop_ms": (I, [c_dp]),
     "sw4b200_grid_set_neighbours": (I, [VP, I, I]),
+    "sw4b200_grid_exchange_transport": (I, [VP]),
     "sw4b200_grid_exchange_begin": (I, [VP, I]),
     "sw4b200_grid_exchange_end": (I, [VP]),
     "sw4b200_measure_fp64_peak": (I, [c_dp, c_dp]),
