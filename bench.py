@@ -305,7 +305,9 @@ def main_ours(a):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        with quiet_stdout():          # (NCCL prints its version banner on stdout when NCCL_DEBUG asks for it: keep stdout to the one line)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
     lib = S.init(local)
     N = world
     strong = a.config == "strong"
@@ -525,7 +527,9 @@ def main_loh1(a):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        with quiet_stdout():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
     lib = S.init(local)
     with quiet_stdout():
         S.lib.comm_init(rank, world)

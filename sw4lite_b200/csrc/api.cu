@@ -1038,23 +1038,18 @@ static void build_sgd_boxes( sw4b200_grid* g )
       g->sgd_boxes->push_back( b );
       g->sgd_zonly->push_back( zonly );
    };
-   // z-active planes: the columns away from the x and y layers only see dcz (most of a production grid's damping
-   // points: the bottom layer) and take the streaming kernel; the x / y layers inside them the general one
+   // The y layers (over the full x extent) and the x layers between them take the general kernel over ALL interior planes in
+   // one launch each (it evaluates the three terms anyway: whether dcz vanishes on a plane makes no difference to it, and a
+   // few tall launches keep the SMs busier than twice as many short ones).  What is left are the columns away from the x and
+   // y layers, where only dcz can be non-zero (most of a production grid's damping points: the bottom layer): they take the
+   // streaming z-only kernel on the z-active planes and nothing at all elsewhere.
+   const std::pair<int, int> fz( w, n[2] - 1 - w );
+   for( auto& y : on[1] ) add( fx, y, fz, 0 );
+   for( auto& y : off[1] )
+      for( auto& x : on[0] ) add( x, y, fz, 0 );
    for( auto& z : on[2] )
-   {
-      for( auto& y : on[1] ) add( fx, y, z, 0 );
       for( auto& y : off[1] )
-      {
-	 for( auto& x : on[0] ) add( x, y, z, 0 );
 	 for( auto& x : off[0] ) add( x, y, z, order == 4 ? 1 : 0 );
-      }
-   }
-   for( auto& z : off[2] )
-   {
-      for( auto& y : on[1] ) add( fx, y, z, 0 );
-      for( auto& y : off[1] )
-	 for( auto& x : on[0] ) add( x, y, z, 0 );
-   }
    g->sgd_boxes_valid = true;
 }
 
