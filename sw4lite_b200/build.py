@@ -19,21 +19,30 @@ def sources():
     return out
 
 
-def build(verbose=True, force=False):
+def build(verbose=True, force=False, out=None, extra=()):
+    """out / extra: a variant of the library under another name with extra nvcc flags (A/B measurements: scripts/ab_variants.sh)"""
     deps = sources()
-    if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
-        return LIB
-    cmd = [NVCC] + FLAGS + ["-o", LIB, os.path.join(SRC, "sw4b200.cu"), "-lcudart"]
+    lib = out or LIB
+    if not force and os.path.exists(lib) and all(os.path.getmtime(d) <= os.path.getmtime(lib) for d in deps):
+        return lib
+    cmd = [NVCC] + FLAGS + list(extra) + ["-o", lib, os.path.join(SRC, "sw4b200.cu"), "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
-    log = os.path.join(HERE, "build.log")
+    log = os.path.join(HERE, "build.log") if out is None else lib + ".log"
     open(log, "w").write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise SystemExit("libsw4b200.so build failed")
     if verbose:
-        print("built", LIB, "(ptxas log in %s)" % log)
-    return LIB
+        print("built", lib, "(ptxas log in %s)" % log)
+    return lib
 
 
 if __name__ == "__main__":
-    build(force="-f" in sys.argv)
+    # python -m sw4lite_b200.build [-f] [-o variant.so -D...]
+    args = [a for a in sys.argv[1:] if a != "-f"]
+    out = None
+    if "-o" in args:
+        n = args.index("-o")
+        out = os.path.abspath(args[n + 1])
+        del args[n:n + 2]
+    build(force="-f" in sys.argv, out=out, extra=args)

@@ -199,7 +199,14 @@ __global__ void k_set_flag( unsigned long long* flag, unsigned long long value )
 __global__ void k_wait_flag( const unsigned long long* flag, unsigned long long value )
 {
    const volatile unsigned long long* f = flag;
-   while( *f < value ) __nanosleep( 200 );
+   const long long t0 = clock64();
+   while( *f < value )
+   {
+      __nanosleep( 200 );
+      // a neighbour that died must not leave this GPU spinning for ever: give up after 2^38 cycles (more than two minutes)
+      // with a device-side trap, which the next CUDA call of this process reports as an error
+      if( clock64() - t0 > ( 1LL << 38 ) ) __trap();
+   }
    __threadfence_system();
 }
 } // namespace

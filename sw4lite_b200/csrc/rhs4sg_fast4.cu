@@ -47,6 +47,17 @@ extern __shared__ __align__( 128 ) double smem_f4[];
 #define F4SM( c ) smem_f4
 #endif
 
+// A/B switches of the march (development; the defaults are the product):
+//   SW4B200_F4_SPLITBAR  1: the block barrier of a step is split into an arrival at the end of step p-1 and a wait in the
+//                           middle of step p (after the in-plane work, which needs nothing from the other warps)
+//   SW4B200_F4_SKEW      1: warps 4..7 start half a step behind warps 0..3 (the two warps of a scheduler out of phase)
+#ifndef SW4B200_F4_SPLITBAR
+#define SW4B200_F4_SPLITBAR 1
+#endif
+#ifndef SW4B200_F4_SKEW
+#define SW4B200_F4_SKEW 1
+#endif
+
 namespace fast4 {
 
 using fast::W4;
@@ -102,8 +113,9 @@ struct Cfg
    static constexpr int O_SX = O_HML + 6 * NH;		      // [PX]
    static constexpr int O_SY = O_SX + PX;		      // [PY]
    static constexpr int O_SZ = O_SY + PY;		      // [SZMAX]
-   static constexpr int O_MBAR = O_SZ + SZMAX;		      // two mbarriers (even / odd planes), 16 bytes apart
-   static constexpr int SMEM_DOUBLES = O_MBAR + 4 + 2;	      // + the tensor-memory base address
+   static constexpr int O_MBAR = O_SZ + SZMAX;		      // mbarriers, 16 bytes apart: +0,+2 planes (even / odd), +4 step, +6 skew
+   static constexpr int O_TMSLOT = O_MBAR + 8;		      // the tensor-memory base address
+   static constexpr int SMEM_DOUBLES = O_TMSLOT + 2;
    static_assert( ( PLANE % 16 ) == 0 && ( O_ML % 16 ) == 0 && ( O_OP % 16 ) == 0 && ( ( TX * TY ) % 16 ) == 0, "TMA destinations: 128-byte aligned" );
    static constexpr int REC = 40;			      // tensor-memory columns per plane record
    static constexpr int COLS = 256;			      // columns per warp of a lane quadrant (8 warps)
@@ -133,6 +145,7 @@ struct Ctx
    int li0, lj0; // local (array) index of the tile's first output
    int tid, txh, ty, o;
    int ka, kb, pend;
+   int nsteps; // steps done so far (split barrier: the step waits for the completion of phase nsteps-1 of the step barrier)
    bool act;  // the left point of the pair is inside the interior
    bool act2; // SPLIT only (rows padded to an even pitch, odd number of points per row): the right point is inside too; without
 	      // padding pairs start at even i and the interior ends at an odd i, so a pair is never split by the boundary
@@ -191,6 +204,19 @@ __device__ __forceinline__ void stage( const FastArgs& a, const FastMaps& maps, 
 
 __device__ __forceinline__ double pick( const D2& v, int t ) { return t ? v.y : v.x; }
 
+// one arrival per warp on the mbarrier at O_MBAR + which (the lanes' shared-memory accesses ordered before it by the warp
+// barrier); the emulation has no warps: every thread arrives
+template <int TY>
+__device__ __forceinline__ void step_arrive( const Ctx<TY>& c, int which )
+{
+#if defined( SW4B200_EMULATE )
+   mbar_arrive( F4SM( c ) + Cfg<TY>::O_MBAR + which );
+#else
+   __syncwarp();
+   if( ( c.tid & 31 ) == 0 ) mbar_arrive( F4SM( c ) + Cfg<TY>::O_MBAR + which );
+#endif
+}
+
 // One step of the march: plane p has been staged into ring slot S.  Does the in-plane work of plane p,
 // the z work of plane k=p-2 (publishing its exchanged products in E buffer S&1) and finishes plane k-1
 // (reading E buffer (S+1)&1).
@@ -205,9 +231,16 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
    const Block& b = a.b;
    const int k = p - 2, kf = p - 3;
 
+#if SW4B200_F4_SPLITBAR && SW4B200_F4_SKEW
+   // the second warp of every scheduler starts once the first has done the in-plane work of its first plane, and stays half a
+   // step behind from then on (each group waits for the other's arrival in the middle of its own step)
+   if( c.nsteps == 0 && c.tid >= NT / 2 ) mbar_wait( F4SM( c ) + C::O_MBAR + 6, 0 );
+#endif
    mbar_wait( F4SM( c ) + C::O_MBAR + 2 * ph.par, ( ph.wpar >> ph.par ) & 1 ); // the boxes of plane p have landed
+#if !SW4B200_F4_SPLITBAR
    __syncthreads(); // the E products of plane k-1 are visible; slot of plane p-5 is free
    stage<TY, EPI>( a, maps, c, p + 1, ph.slot == NSLOT - 1 ? 0 : ph.slot + 1, ph.par ^ 1 );
+#endif
    tm.wait_st(); // the records stored by the earlier steps (long done) are readable
 
    const bool kfin = kf >= c.ka && kf <= c.kb;
@@ -405,6 +438,16 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
    tm.template ld<16, 8>( tq + 2, ph.c[2] );	 // pr1 pr2 e1 e2
    tm.template ld<32, 4>( tq + 10, ph.c[2] ); // e4 e5
 
+#if SW4B200_F4_SPLITBAR
+   // every warp has finished step p-1: the E products of plane k-1 are visible, the slot of plane p-5 (and the mu/la slot
+   // and operand buffer of the other parity) is free.  The in-plane work above needed none of that, so a warp only waits
+   // here if another one is more than that work behind.
+#if SW4B200_F4_SKEW
+   if( c.nsteps == 0 && c.tid < NT / 2 ) step_arrive<TY>( c, 6 );
+#endif
+   if( c.nsteps > 0 ) mbar_wait( F4SM( c ) + C::O_MBAR + 4, ( c.nsteps - 1 ) & 1 );
+   stage<TY, EPI>( a, maps, c, p + 1, ph.slot == NSLOT - 1 ? 0 : ph.slot + 1, ph.par ^ 1 );
+#endif
    const double szk = k >= c.p0 ? F4SM( c )[C::O_SZ + k - c.p0] : 0.0;
    auto helper = [&]() {
       // ring of width 2 around the tile: the same products recomputed from the staged planes
@@ -509,6 +552,10 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
 
    }
    helper();
+#if SW4B200_F4_SPLITBAR
+   step_arrive<TY>( c, 4 );
+   c.nsteps++;
+#endif
 
 #pragma unroll
    for( int m = 0; m < 3; m++ ) { s.rp[m][0] = rnew[m][0]; s.rp[m][1] = rnew[m][1]; }
@@ -540,19 +587,27 @@ __global__ void __launch_bounds__( 16 * TY, 1 ) k_rhs_fast4( const FastArgs a, c
    c.kb = ( c.ka + a.kchunk - 1 < a.khi ) ? c.ka + a.kchunk - 1 : a.khi;
    if( c.ka > c.kb ) return;
    c.pend = c.kb + 2;
+   c.nsteps = 0;
 
    fast4::Tm tm;
    if( c.tid == 0 )
    {
       mbar_init( smem + C::O_MBAR, 1 );
       mbar_init( smem + C::O_MBAR + 2, 1 );
+#if defined( SW4B200_EMULATE )
+      mbar_init( smem + C::O_MBAR + 4, NT );
+      mbar_init( smem + C::O_MBAR + 6, NT / 2 );
+#else
+      mbar_init( smem + C::O_MBAR + 4, NT / 32 );
+      mbar_init( smem + C::O_MBAR + 6, NT / 64 );
+#endif
 #if !defined( SW4B200_EMULATE )
       asm volatile( "fence.mbarrier_init.release.cluster;" ::: "memory" );
 #endif
    }
 #if !defined( SW4B200_EMULATE )
    // all 512 columns of tensor memory: one CTA per SM (shared memory), so nobody else can want them
-   uint32_t* const tm_slot = reinterpret_cast<uint32_t*>( smem + C::O_MBAR + 4 );
+   uint32_t* const tm_slot = reinterpret_cast<uint32_t*>( smem + C::O_TMSLOT );
    if( c.tid < 32 )
    {
       asm volatile( "tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"( (uint32_t)__cvta_generic_to_shared( tm_slot ) )

@@ -50,6 +50,7 @@ __device__ __forceinline__ void mbar_arrive_expect( double* m, int ) // (the emu
       b->phase.fetch_add( 1 );
    }
 }
+__device__ __forceinline__ void mbar_arrive( double* m ) { mbar_arrive_expect( m, 0 ); }
 __device__ __forceinline__ void mbar_wait( double* m, int parity )
 {
    EmuBar* b = reinterpret_cast<EmuBar*>( m );
@@ -76,6 +77,12 @@ __device__ __forceinline__ void mbar_arrive_expect( double* mbar, int bytes )
 {
    asm volatile( "mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"( (uint32_t)__cvta_generic_to_shared( mbar ) ), "r"( bytes )
 		 : "memory" );
+}
+// plain arrival (release at CTA scope: what the thread, and the threads it synchronised with, wrote to shared memory before
+// is visible to whoever sees the phase complete)
+__device__ __forceinline__ void mbar_arrive( double* mbar )
+{
+   asm volatile( "mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"( (uint32_t)__cvta_generic_to_shared( mbar ) ) : "memory" );
 }
 __device__ __forceinline__ void mbar_wait( double* mbar, int parity )
 {

@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(HERE, "libsw4b200.so")
+# (SW4B200_LIB: a variant build of the same library, for A/B measurements of kernel changes)
+LIBPATH = os.environ.get("SW4B200_LIB") or os.path.join(HERE, "libsw4b200.so")
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int)
