@@ -219,7 +219,10 @@ int sw4b200_grid_destroy( sw4b200_grid* g );
  * "bforce0".."bforce5" (3*points of the side window).  Host arrays are always in the reference's
  * Sarray layout (Sarray.C:753-778) with npts = ni*nj*nk.  On the device the rows of an (i,j,k,c) block with odd
  * ni are padded to an even pitch (sw4b200_grid_row_pitch doubles; 16-byte aligned rows for the TMA-staged
- * kernels): upload/download convert, code that uses sw4b200_grid_device_ptr must honour the pitch. */
+ * kernels): upload/download convert, code that uses sw4b200_grid_device_ptr must honour the pitch.
+ * Materials are time-invariant: the block keeps 2 mu + lambda and 1 / rho next to them for its fused passes and refreshes
+ * the two after sw4b200_grid_upload / _fill_profile / _device_ptr of "mu", "lambda" or "rho" -- code that writes the materials
+ * through a device pointer AFTER the first time step must ask for the pointer again (or upload) afterwards. */
 int sw4b200_grid_upload( sw4b200_grid* g, const char* name, const double* h_src );
 int sw4b200_grid_download( sw4b200_grid* g, const char* name, double* h_dst );
 void* sw4b200_grid_device_ptr( sw4b200_grid* g, const char* name );

@@ -146,7 +146,7 @@ static void fast_args( const RhsArgs& a, FastArgs& f )
    for( int c = 0; c < 3; c++ ) f.u[c] = a.u + c * a.b.npts;
    f.mu = a.mu; f.la = a.la; f.strx = a.strx; f.stry = a.stry; f.strz = a.strz;
    f.cof6 = 1.0 / ( 6 * a.h * a.h ); f.cof144 = 1.0 / ( 144 * a.h * a.h );
-   f.rho = a.rho;
+   f.rho = a.rho; f.la2 = a.la2; f.rhoi = a.rhoi;
    for( int c = 0; c < 3; c++ )
    {
       f.out[c] = a.out + c * a.b.npts;
@@ -259,6 +259,10 @@ struct sw4b200_grid
    cudaStream_t st;
    double *U, *Um, *Up, *Uacc; // Uacc: stored acceleration (SoA fast path) / second Up buffer (general path)
    double *mu, *la, *rho, *jac, *met;
+   // derived from mu, la, rho for the fused passes of the SoA fast path (2 mu + lambda, 1 / rho): allocated and filled before the
+   // first pass that wants them, refilled after any call that can have changed the materials (upload, fill_profile, device_ptr)
+   double *la2, *rhoi;
+   bool derived_valid;
    double* Lu;		       // curvilinear blocks: L(u) scratch of the unfused sequence
    double* flux;	       // curvilinear blocks: the 9 flux arrays of the two-sweep operator (curvilinear.cu)
    bool fast;		       // SoA Cartesian throughput path
@@ -805,7 +809,7 @@ int sw4b200_grid_destroy( sw4b200_grid* g )
 {
    if( !g ) return 0;
    cudaStreamSynchronize( g->st );
-   double* ptrs[] = { g->U, g->Um, g->Up, g->Uacc, g->mu, g->la, g->rho, g->jac, g->met, g->d_f, g->d_rec,
+   double* ptrs[] = { g->U, g->Um, g->Up, g->Uacc, g->mu, g->la, g->rho, g->la2, g->rhoi, g->jac, g->met, g->d_f, g->d_rec,
 		      g->d_fser, g->d_fttser, g->d_recser, g->Lu, g->flux };
    for( int d = 0; d < 3; d++ ) delete g->h_dc[d];
    delete g->sgd_boxes;
@@ -831,6 +835,7 @@ int sw4b200_grid_upload( sw4b200_grid* g, const char* name, const double* h_src 
    double** p = grid_array( g, name, &n, &nc );
    if( !p || !*p ) return set_error( "grid_upload: unknown or unallocated array '%s'", name );
    if( grid_copy( g, *p, const_cast<double*>( h_src ), n, nc, true ) ) return 1;
+   if( p == &g->mu || p == &g->la || p == &g->rho ) g->derived_valid = false;
    for( int d = 0; d < 3; d++ )
       if( p == &g->dc[d] )
       {
@@ -852,6 +857,7 @@ void* sw4b200_grid_device_ptr( sw4b200_grid* g, const char* name )
    size_t n = 0;
    int nc = 0;
    double** p = grid_array( g, name, &n, &nc );
+   if( p == &g->mu || p == &g->la || p == &g->rho ) g->derived_valid = false; // (the caller may write through the pointer)
    return p ? (void*)*p : 0;
 }
 size_t sw4b200_grid_array_size( sw4b200_grid* g, const char* name )
@@ -915,6 +921,18 @@ int sw4b200_grid_set_receiver_points( sw4b200_grid* g, int n, const int* ijk )
    return 0;
 }
 
+// the derived coefficient arrays of a fast-path block, up to date
+static int ensure_derived( sw4b200_grid* g )
+{
+   if( !g->fast || g->derived_valid ) return 0;
+   const size_t np = (size_t)g->b.npts;
+   if( !g->la2 && !( g->la2 = (double*)sw4b200_malloc( np * 8 ) ) ) return 1;
+   if( !g->rhoi && !( g->rhoi = (double*)sw4b200_malloc( np * 8 ) ) ) return 1;
+   if( launch_derive_materials( (long long)np, g->mu, g->la, g->rho, g->la2, g->rhoi, g->st ) ) return 1;
+   g->derived_valid = true;
+   return 0;
+}
+
 static void fill_args( sw4b200_grid* g, RhsArgs& a )
 {
    memset( &a, 0, sizeof( a ) );
@@ -923,6 +941,7 @@ static void fill_args( sw4b200_grid* g, RhsArgs& a )
    a.onesided4 = g->d.onesided[4] == 1;
    a.onesided5 = g->d.onesided[5] == 1;
    a.mu = g->mu; a.la = g->la; a.rho = g->rho;
+   if( g->fast && g->derived_valid ) { a.la2 = g->la2; a.rhoi = g->rhoi; }
    a.strx = g->str[0]; a.stry = g->str[1]; a.strz = g->str[2];
    a.dcx = g->dc[0]; a.dcy = g->dc[1]; a.dcz = g->dc[2];
    a.cox = g->co[0]; a.coy = g->co[1]; a.coz = g->co[2];
@@ -987,6 +1006,7 @@ static int curv_corrector_dev( sw4b200_grid* g, const double* d_ftt );
 static int predictor_dev( sw4b200_grid* g, int part )
 {
    RhsArgs a;
+   if( ensure_derived( g ) ) return 1;
    fill_args( g, a );
    a.out = g->Up; a.u = g->U; a.um = g->Um; a.fo = 0;
    if( !g->fast )
@@ -1084,6 +1104,7 @@ static int damping_dev( sw4b200_grid* g, int part )
 static int corrector_dev( sw4b200_grid* g, int part )
 {
    RhsArgs a;
+   if( ensure_derived( g ) ) return 1;
    fill_args( g, a );
    if( !g->fast )
    {
@@ -1429,6 +1450,7 @@ int sw4b200_grid_fill_profile( sw4b200_grid* g, const char* name, const double* 
    double* d_prof = 0;
    CUDA_OK( cudaMalloc( (void**)&d_prof, g->b.nk * sizeof( double ) ) );
    CUDA_OK( cudaMemcpy( d_prof, h_kvalues, g->b.nk * sizeof( double ), cudaMemcpyHostToDevice ) );
+   if( p == &g->mu || p == &g->la || p == &g->rho ) g->derived_valid = false;
    const int rc = launch_fill_profile( g->b, *p, d_prof, g->st );
    CUDA_OK( cudaStreamSynchronize( g->st ) );
    cudaFree( d_prof );

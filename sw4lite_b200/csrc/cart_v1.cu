@@ -1250,6 +1250,23 @@ int launch_gather_points( int corder, long long npts, const double* u, int n, co
    count_launch();
    return check_launch( "k_gather_points" );
 }
+// derived, time-invariant coefficient arrays of a grid block (read by the fused passes of rhs4sg_fast4.cu instead of lambda, rho):
+// 2 mu + lambda in ONE rounding (2 mu is exact; the same value every kernel forms with fma( 2, mu, lambda )) and 1 / rho (IEEE division)
+__global__ void k_derive_materials( long long n, const double* __restrict__ mu, const double* __restrict__ la, const double* __restrict__ rho,
+				    double* __restrict__ la2, double* __restrict__ rhoi )
+{
+   for( long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x )
+   {
+      la2[t] = fma( 2.0, mu[t], la[t] );
+      rhoi[t] = 1.0 / rho[t];
+   }
+}
+int launch_derive_materials( long long n, const double* mu, const double* la, const double* rho, double* la2, double* rhoi, cudaStream_t st )
+{
+   k_derive_materials<<<nblocks( n, 256 ), 256, 0, st>>>( n, mu, la, rho, la2, rhoi );
+   count_launch();
+   return check_launch( "k_derive_materials" );
+}
 int launch_fill_profile( const Block& b, double* a, const double* prof, cudaStream_t st )
 {
    k_fill_profile<<<nblocks( b.npts, 256 ), 256, 0, st>>>( b, a, prof );

@@ -83,6 +83,7 @@ struct RhsArgs
    double* out2;    // PRED: uacc = (L(u)/h^2+fo)/rho (optional); SHELL_DPDMT: uacc
    const double *u, *um, *up; // PRED: u,um ; CORR: up,u,um (uacc formed on the fly); LU: u
    const double *mu, *la, *rho, *fo;
+   const double *la2, *rhoi; // derived arrays of a grid block: 2 mu + lambda, 1 / rho (null: caller-owned arrays)
    const double *strx, *stry, *strz;
    double h, dt;
    // supergrid damping fused into MODE_CORR when sg_order != 0
@@ -125,6 +126,7 @@ int launch_add_point_forces( int corder, long long npts, double* up, const doubl
 int launch_gather_points( int corder, long long npts, const double* u, int n, const long long* pidx,
 			  double* out, cudaStream_t st );
 int launch_fill_profile( const Block& b, double* a, const double* prof, cudaStream_t st );
+int launch_derive_materials( long long n, const double* mu, const double* la, const double* rho, double* la2, double* rhoi, cudaStream_t st );
 int launch_halo_copy( const Block& b, double* field, int kplane, double* buf, int pack, cudaStream_t st );
 
 // curvilinear (curvilinear.cu)

@@ -15,6 +15,10 @@ struct FastArgs
    int kchunk;	     // planes per CTA in z
    const double* u[3];	 // input field (u for LU/PRED, uacc for CORR), halo'd reads
    const double *mu, *la;
+   // derived, time-invariant coefficient arrays of a grid block (api.cu keeps them next to mu, la, rho): 2 mu + lambda and
+   // 1 / rho.  The TMA kernel's fused passes read THESE instead of lambda and rho (13 fp64 instructions per point less);
+   // null for caller-owned arrays, whose fused passes take the cp.async kernel
+   const double *la2, *rhoi;
    const double *strx, *stry, *strz;
    double cof6, cof144; // 1/(6 h^2), 1/(144 h^2)
    // epilogue

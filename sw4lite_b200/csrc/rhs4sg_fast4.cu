@@ -48,6 +48,12 @@ extern __shared__ __align__( 128 ) double smem_f4[];
 #endif
 
 namespace fast4 {
+// DER (template parameter of the kernel): the staged "lambda" plane and the "rho" operand hold the derived, time-invariant
+// arrays 2 mu + lambda and 1 / rho of a grid block (FastArgs::la2, rhoi).  2 mu + lambda is then read instead of formed at
+// every use (3 + 5 + 1 times per point), lambda itself is recovered where the operator needs it (own point: one fma; 2 mu is
+// exact, so lambda comes back to within one rounding of 2 mu + lambda), and the epilogue multiplies by the stored reciprocal.
+template <bool DER>
+__device__ __forceinline__ double bsum( double m, double l ) { return DER ? l : 2 * m + l; } // 2 mu + lambda
 
 using fast::W4;
 using fast::weights4;
@@ -194,7 +200,7 @@ __device__ __forceinline__ double pick( const D2& v, int t ) { return t ? v.y : 
 // One step of the march: plane p has been staged into ring slot S.  Does the in-plane work of plane p,
 // the z work of plane k=p-2 (publishing its exchanged products in E buffer S&1) and finishes plane k-1
 // (reading E buffer (S+1)&1).
-template <int TY, int EPI, int SPLIT, int H>
+template <int TY, int EPI, int SPLIT, bool DER, int H>
 __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, Ctx<TY>& c, State& s, Tm& tm, const int p, const Ph& ph )
 {
    typedef Cfg<TY> C;
@@ -240,11 +246,11 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
 	    const double rh = fin ? pick( e_rho, t ) : 1.0;
 	    if( EPI == EPI_PRED )
 	    {
-	       rinv[t] = rcp_nr( rh ); // one reciprocal per point; dt^2/rho and acc/rho are formed from it
+	       rinv[t] = DER ? rh : rcp_nr( rh ); // one reciprocal per point; dt^2/rho and acc/rho are formed from it
 	       fr[t] = a.fac * rinv[t];
 	    }
 	    else
-	       fr[t] = a.fac * rcp_nr( rh );
+	       fr[t] = a.fac * ( DER ? rh : rcp_nr( rh ) );
 	 }
       }
       constexpr int RF = R3; // plane kf = p-3
@@ -306,7 +312,7 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
       const double* const pl = sm + C::O_ML + ( 1 * 2 + ML ) * PLANE + c.o;
       const double szp = sm[C::O_SZ + p - c.p0];
       double rec[14]; // pr0A pr0B pr1A pr1B pr2A pr2B e1A e1B e2A e2B e4A e4B e5A e5B
-      double m0[2], l0[2], q0[3][2], dx[3][2], dy[3][2];
+      double m0[2], l0[2], b0[2], q0[3][2], dx[3][2], dy[3][2];
       {
 	 // x-direction coefficients mu sx, (2mu+la) sx at i-2..i+3, shared by the two points
 	 double axm[6], axl[6];
@@ -315,10 +321,12 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
 #pragma unroll
 	 for( int f = 0; f < 3; f++ ) { xa[f] = ld2( pf[f] - 2 ); xb[f] = ld2( pf[f] ); xc[f] = ld2( pf[f] + 2 ); }
 	 {
-	    m0[0] = mb.x; m0[1] = mb.y; l0[0] = lb.x; l0[1] = lb.y;
+	    m0[0] = mb.x; m0[1] = mb.y;
+	    b0[0] = bsum<DER>( mb.x, lb.x ); b0[1] = bsum<DER>( mb.y, lb.y );
+	    l0[0] = DER ? fma( -2.0, mb.x, lb.x ) : lb.x; l0[1] = DER ? fma( -2.0, mb.y, lb.y ) : lb.y;
 	    axm[0] = ma.x * csx[0]; axm[1] = ma.y * csx[1]; axm[2] = mb.x * csx[2]; axm[3] = mb.y * csx[3]; axm[4] = mc.x * csx[4]; axm[5] = mc.y * csx[5];
-	    axl[0] = ( 2 * ma.x + la.x ) * csx[0]; axl[1] = ( 2 * ma.y + la.y ) * csx[1]; axl[2] = ( 2 * mb.x + lb.x ) * csx[2];
-	    axl[3] = ( 2 * mb.y + lb.y ) * csx[3]; axl[4] = ( 2 * mc.x + lc.x ) * csx[4]; axl[5] = ( 2 * mc.y + lc.y ) * csx[5];
+	    axl[0] = bsum<DER>( ma.x, la.x ) * csx[0]; axl[1] = bsum<DER>( ma.y, la.y ) * csx[1]; axl[2] = b0[0] * csx[2];
+	    axl[3] = b0[1] * csx[3]; axl[4] = bsum<DER>( mc.x, lc.x ) * csx[4]; axl[5] = bsum<DER>( mc.y, lc.y ) * csx[5];
 	 }
 	 W4 wmx[2], wlx[2];
 #pragma unroll
@@ -344,7 +352,7 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
       for( int t = 0; t < 2; t++ )
       {
 	 s.cu[R0][t] = q0[0][t]; s.cv[R0][t] = q0[1][t]; s.cw[R0][t] = q0[2][t];
-	 s.amz[R0][t] = m0[t] * szp; s.alz[R0][t] = ( 2 * m0[t] + l0[t] ) * szp;
+	 s.amz[R0][t] = m0[t] * szp; s.alz[R0][t] = b0[t] * szp;
       }
       {
 	 W4 wmy[2], wly[2];
@@ -357,8 +365,8 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
 	       const double mym2 = pick( ma, t ), mym1 = pick( mb, t ), myp1 = pick( mc, t ), myp2 = pick( md, t );
 	       const double lym2 = pick( la, t ), lym1 = pick( lb, t ), lyp1 = pick( lc, t ), lyp2 = pick( ld, t );
 	       wmy[t] = weights4( mym2 * csy[0], mym1 * csy[1], m0[t] * syo, myp1 * csy[3], myp2 * csy[4] );
-	       wly[t] = weights4( ( 2 * mym2 + lym2 ) * csy[0], ( 2 * mym1 + lym1 ) * csy[1], ( 2 * m0[t] + l0[t] ) * syo,
-				  ( 2 * myp1 + lyp1 ) * csy[3], ( 2 * myp2 + lyp2 ) * csy[4] );
+	       wly[t] = weights4( bsum<DER>( mym2, lym2 ) * csy[0], bsum<DER>( mym1, lym1 ) * csy[1], b0[t] * syo, bsum<DER>( myp1, lyp1 ) * csy[3],
+				  bsum<DER>( myp2, lyp2 ) * csy[4] );
 	    }
 	 }
 #pragma unroll
@@ -427,7 +435,8 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
 	 }
 	 const int oo = sy_ * PX + sx_;
 	 hml[ph.t0 + hh] = F4SM( c )[C::O_ML + ( 0 * 2 + ML ) * PLANE + oo];
-	 hml[ph.t0 + NH + hh] = F4SM( c )[C::O_ML + ( 1 * 2 + ML ) * PLANE + oo];
+	 hml[ph.t0 + NH + hh] = DER ? fma( -2.0, hml[ph.t0 + hh], F4SM( c )[C::O_ML + ( 1 * 2 + ML ) * PLANE + oo] )
+				    : F4SM( c )[C::O_ML + ( 1 * 2 + ML ) * PLANE + oo];
 	 const double hm = hml[ph.t2 + hh], hl = hml[ph.t2 + NH + hh];
 	 const double* const qu = sf + 0 * NSLOT * PLANE + ph.o[2] + oo;
 	 const double* const qv = sf + 1 * NSLOT * PLANE + ph.o[2] + oo;
@@ -516,7 +525,7 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
 
 } // namespace fast4
 
-template <int TY, int EPI, int SPLIT>
+template <int TY, int EPI, int SPLIT, bool DER>
 __global__ void __launch_bounds__( 16 * TY, 1 ) k_rhs_fast4( const FastArgs a, const SW4_GRID_CONSTANT FastMaps maps )
 {
    using namespace fast4;
@@ -661,15 +670,15 @@ __global__ void __launch_bounds__( 16 * TY, 1 ) k_rhs_fast4( const FastArgs a, c
    int p = c.ka - 2;
    if( p & 1 )
    {
-      fast4::step<TY, EPI, SPLIT, 1>( a, maps, c, s, tm, p, ph );
+      fast4::step<TY, EPI, SPLIT, DER, 1>( a, maps, c, s, tm, p, ph );
       shift2(); next_plane(); p++;
    }
    while( p <= plast )
    {
-      fast4::step<TY, EPI, SPLIT, 0>( a, maps, c, s, tm, p, ph );
+      fast4::step<TY, EPI, SPLIT, DER, 0>( a, maps, c, s, tm, p, ph );
       next_plane(); p++;
       if( p > plast ) break;
-      fast4::step<TY, EPI, SPLIT, 1>( a, maps, c, s, tm, p, ph );
+      fast4::step<TY, EPI, SPLIT, DER, 1>( a, maps, c, s, tm, p, ph );
       shift2(); next_plane(); p++;
    }
 #if !defined( SW4B200_EMULATE )
@@ -682,7 +691,7 @@ __global__ void __launch_bounds__( 16 * TY, 1 ) k_rhs_fast4( const FastArgs a, c
 
 #ifndef SW4B200_EMULATE
 namespace {
-template <int TY, int EPI, int SPLIT>
+template <int TY, int EPI, int SPLIT, bool DER>
 int launch_fast4_t( FastArgs a, cudaStream_t st )
 {
    typedef fast4::Cfg<TY> C;
@@ -690,7 +699,7 @@ int launch_fast4_t( FastArgs a, cudaStream_t st )
    const size_t smem = C::SMEM_DOUBLES * sizeof( double );
    if( !configured )
    {
-      cudaError_t e = cudaFuncSetAttribute( k_rhs_fast4<TY, EPI, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem );
+      cudaError_t e = cudaFuncSetAttribute( k_rhs_fast4<TY, EPI, SPLIT, DER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem );
       if( e != cudaSuccess ) return set_error( "k_rhs_fast4: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString( e ) );
       configured = true;
    }
@@ -701,17 +710,17 @@ int launch_fast4_t( FastArgs a, cudaStream_t st )
    memset( &maps, 0, sizeof( maps ) );
    for( int f = 0; f < 3; f++ )
       if( make_tmap( &maps.u[f], a.u[f], b, C::PX, C::PY ) ) return 1;
-   if( make_tmap( &maps.mu, a.mu, b, C::PX, C::PY ) || make_tmap( &maps.la, a.la, b, C::PX, C::PY ) ) return 1;
+   if( make_tmap( &maps.mu, a.mu, b, C::PX, C::PY ) || make_tmap( &maps.la, DER ? a.la2 : a.la, b, C::PX, C::PY ) ) return 1;
    if( EPI != EPI_LU )
    {
-      if( make_tmap( &maps.rho, a.rho, b, C::TX, TY ) ) return 1;
+      if( make_tmap( &maps.rho, DER ? a.rhoi : a.rho, b, C::TX, TY ) ) return 1;
       for( int f = 0; f < 3; f++ )
 	 if( make_tmap( &maps.um[f], a.um[f], b, C::TX, TY ) ) return 1;
    }
    dim3 bs( C::NT, 1, 1 );
    dim3 gs( ( b.nil - 4 + C::TX - 1 ) / C::TX, ( b.nj - 4 + TY - 1 ) / TY, ( a.khi - a.klo + 1 + a.kchunk - 1 ) / a.kchunk );
    ProfScope prof( EPI == EPI_PRED ? "rhs_fast_pred" : ( EPI == EPI_CORR ? "rhs_fast_corr" : "rhs_fast_lu" ), st );
-   k_rhs_fast4<TY, EPI, SPLIT><<<gs, bs, smem, st>>>( a, maps );
+   k_rhs_fast4<TY, EPI, SPLIT, DER><<<gs, bs, smem, st>>>( a, maps );
    count_launch();
    return check_launch( "k_rhs_fast4" );
 }
@@ -726,7 +735,7 @@ int launch_fast4( int epi, const FastArgs& a, cudaStream_t st )
    // (the operator-level entry points on the reference's own layout) take the cp.async kernel of the second generation; grid
    // blocks (sw4b200_grid_create) pad their rows to an even pitch and stay here.
    uintptr_t al = (uintptr_t)a.u[0] | (uintptr_t)a.u[1] | (uintptr_t)a.u[2] | (uintptr_t)a.mu | (uintptr_t)a.la;
-   if( epi != EPI_LU ) al |= (uintptr_t)a.rho | (uintptr_t)a.um[0] | (uintptr_t)a.um[1] | (uintptr_t)a.um[2];
+   if( epi != EPI_LU ) al |= (uintptr_t)a.rho | (uintptr_t)a.um[0] | (uintptr_t)a.um[1] | (uintptr_t)a.um[2] | (uintptr_t)a.la2 | (uintptr_t)a.rhoi;
    al |= (uintptr_t)a.out[0] | (uintptr_t)a.out[1] | (uintptr_t)a.out[2];
    if( epi == EPI_PRED && a.out2[0] ) al |= (uintptr_t)a.out2[0] | (uintptr_t)a.out2[1] | (uintptr_t)a.out2[2];
    if( ( a.b.ni & 1 ) || ( al & 15 ) ) return launch_fast2( epi, a, st );
@@ -735,20 +744,22 @@ int launch_fast4( int epi, const FastArgs& a, cudaStream_t st )
    // injected sparsely, pass A always stores uacc): the operator-level calls that use them take the cp.async kernel too
    if( epi != EPI_LU && a.fo[0] ) return launch_fast2( epi, a, st );
    if( epi == EPI_PRED && !a.out2[0] ) return launch_fast2( epi, a, st );
+   // the fused passes of this kernel exist for the derived coefficient arrays of a grid block only
+   if( epi != EPI_LU && ( !a.la2 || !a.rhoi ) ) return launch_fast2( epi, a, st );
    // grid blocks with an odd number of points per row are allocated with rows padded to an even pitch (api.cu): the last pair of
    // a row is then split by the boundary (SPLIT variant: that pair stores its left point only)
    if( a.b.nil != a.b.ni )
       switch( epi )
       {
-      case EPI_LU: return launch_fast4_t<16, EPI_LU, 1>( a, st );
-      case EPI_PRED: return launch_fast4_t<16, EPI_PRED, 1>( a, st );
-      default: return launch_fast4_t<16, EPI_CORR, 1>( a, st );
+      case EPI_LU: return launch_fast4_t<16, EPI_LU, 1, false>( a, st );
+      case EPI_PRED: return launch_fast4_t<16, EPI_PRED, 1, true>( a, st );
+      default: return launch_fast4_t<16, EPI_CORR, 1, true>( a, st );
       }
    switch( epi )
    {
-   case EPI_LU: return launch_fast4_t<16, EPI_LU, 0>( a, st );
-   case EPI_PRED: return launch_fast4_t<16, EPI_PRED, 0>( a, st );
-   default: return launch_fast4_t<16, EPI_CORR, 0>( a, st );
+   case EPI_LU: return launch_fast4_t<16, EPI_LU, 0, false>( a, st );
+   case EPI_PRED: return launch_fast4_t<16, EPI_PRED, 0, true>( a, st );
+   default: return launch_fast4_t<16, EPI_CORR, 0, true>( a, st );
    }
 }
 #endif

@@ -32,6 +32,7 @@ extern "C" int emu_rhs_fast( int gen, int epi, int ifirst, int ilast, int jfirst
       a.um[c] = um ? um + c * n : 0;
       a.fo[c] = fo ? fo + c * n : 0;
    }
+   a.la2 = a.rhoi = 0;
    a.mu = mu; a.la = la; a.strx = strx; a.stry = stry; a.strz = strz; a.cof6 = cof / 6; a.cof144 = cof / 144; a.rho = rho; a.fac = fac;
    if( gen == 4 )
    {
@@ -41,18 +42,26 @@ extern "C" int emu_rhs_fast( int gen, int epi, int ifirst, int ilast, int jfirst
       dim3 gs( ( a.b.nil - 4 + C4::TX - 1 ) / C4::TX, ( a.b.nj - 4 + TY4 - 1 ) / TY4, ( khi - klo + 1 + kchunk - 1 ) / kchunk );
       FastMaps maps; // (the emulated TMA tile load reads through the array base)
       for( int c = 0; c < 3; c++ ) { maps.u[c].base = a.u[c]; maps.um[c].base = a.um[c]; }
-      maps.mu.base = a.mu; maps.la.base = a.la; maps.rho.base = a.rho;
+      // the fused passes read the derived arrays of a grid block (2 mu + lambda, 1 / rho: launch_derive_materials)
+      std::vector<double> la2, rhoi;
+      if( epi != EPI_LU )
+      {
+	 la2.resize( n ); rhoi.resize( n );
+	 for( long long q = 0; q < n; q++ ) { la2[q] = 2 * mu[q] + la[q]; rhoi[q] = 1.0 / rho[q]; }
+	 a.la2 = la2.data(); a.rhoi = rhoi.data();
+      }
+      maps.mu.base = a.mu; maps.la.base = epi != EPI_LU ? a.la2 : a.la; maps.rho.base = epi != EPI_LU ? a.rhoi : a.rho;
       if( a.b.nil == a.b.ni )
       {
-	 if( epi == EPI_LU ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_LU, 0>( a, maps ); } );
-	 else if( epi == EPI_PRED ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_PRED, 0>( a, maps ); } );
-	 else emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_CORR, 0>( a, maps ); } );
+	 if( epi == EPI_LU ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_LU, 0, false>( a, maps ); } );
+	 else if( epi == EPI_PRED ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_PRED, 0, true>( a, maps ); } );
+	 else emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_CORR, 0, true>( a, maps ); } );
       }
       else
       {
-	 if( epi == EPI_LU ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_LU, 1>( a, maps ); } );
-	 else if( epi == EPI_PRED ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_PRED, 1>( a, maps ); } );
-	 else emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_CORR, 1>( a, maps ); } );
+	 if( epi == EPI_LU ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_LU, 1, false>( a, maps ); } );
+	 else if( epi == EPI_PRED ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_PRED, 1, true>( a, maps ); } );
+	 else emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_CORR, 1, true>( a, maps ); } );
       }
       return 0;
    }
