@@ -445,6 +445,13 @@ def main_ours(a):
         lib.sw4b200_profile_read(name.encode(), C.byref(tot), C.byref(cnt))
         if cnt.value:
             prof[name] = {"ms_per_step": tot.value / a.steps, "launches_per_step": cnt.value / a.steps}
+    tiles = {}
+    for name in ("tiles_plain", "tiles_general"):   # thread blocks of the interior kernel without / with stretching factors
+        tot = C.c_double(0); cnt = C.c_longlong(0)
+        lib.sw4b200_profile_read(name.encode(), C.byref(tot), C.byref(cnt))
+        tiles[name] = cnt.value
+    if tiles["tiles_plain"] + tiles["tiles_general"]:
+        prof["interior_tiles"] = {"plain_frac": tiles["tiles_plain"] / (tiles["tiles_plain"] + tiles["tiles_general"])}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -44,7 +44,9 @@ int sw4b200_sync_device( void );
 int sw4b200_kernel_launch_count( void );   /* number of kernels launched by this library so far */
 /* per-kernel device time, measured with CUDA events on the launching stream (the timing hooks of
  * EW::timesteploop's time_measure[], EW.C:2529-2873, at kernel granularity).  Names: "rhs_fast_pred",
- * "rhs_fast_corr", "rhs_fast_lu", "rhs_v1", "addsgd", "shell", "bc". */
+ * "rhs_fast_corr", "rhs_fast_lu", "rhs_v1", "addsgd", "shell", "bc".  "tiles_plain" / "tiles_general": no time, `launches` =
+ * thread blocks of the interior kernel since the last reset that ran the march without / with the stretching factors
+ * (tiles on which strx = stry = 1 / the others). */
 int sw4b200_profile_enable( int on );
 int sw4b200_profile_reset( void );
 int sw4b200_profile_read( const char* kernel, double* ms_total, long long* launches );

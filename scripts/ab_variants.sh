@@ -13,7 +13,7 @@ for v in "$@"; do
 import json
 try:
     d = json.loads(open("gpurun_out/abv_${tag}_$n.json").read().strip().splitlines()[-1])
-    print("$n: %.2f ms/step %.2f Gpts/s " % (d["ms_per_step"], d["value"]), {k: round(x["ms_per_step"], 2) for k, x in d["kernels"].items()}, d["clocks"]["sm_mhz"])
+    print("$n: %.2f ms/step %.2f Gpts/s " % (d["ms_per_step"], d["value"]), {k: round(x.get("ms_per_step", x.get("plain_frac", 0)), 2) for k, x in d["kernels"].items()}, d["clocks"]["sm_mhz"])
 except Exception as e:
     print("$n: no result", e)
 PY

@@ -14,6 +14,7 @@
 namespace sw4b200 {
 
 int measure_fp64_peak( double* tflops, double* fma_per_s, cudaStream_t st ); // peaks.cu
+int read_f4_tiles( long long out[2], bool reset );				   // rhs4sg_fast4.cu
 // exchange.cu
 int comm_unique_id( void* out128 );
 int comm_init( int rank, int nranks, const void* id128 );
@@ -28,6 +29,10 @@ int exchange_group_end();
 static thread_local char g_err[1024] = "";
 static int g_launches = 0;
 static cudaStream_t g_streams[4] = { 0, 0, 0, 0 };
+// auxiliary stream for a launch that is independent of the one before it on the same stream (the two launches of a fused pass,
+// rhs4sg_fast4.cu): forked from and joined to the caller's stream by events, so callers still see one stream
+static cudaStream_t g_aux = 0;
+static cudaEvent_t g_ev_fork = 0, g_ev_join = 0;
 static bool g_init = false;
 static int g_device = -1;
 
@@ -47,6 +52,20 @@ int check_launch( const char* what )
 }
 void count_launch( int n ) { g_launches += n; }
 cudaStream_t as_stream( void* s ) { return s ? (cudaStream_t)s : g_streams[0]; }
+// the auxiliary stream, ordered after everything queued on st so far (0 if it cannot be had: the caller then stays on st)
+cudaStream_t aux_fork( cudaStream_t st )
+{
+   if( !g_aux || st == g_aux ) return 0;
+   if( cudaEventRecord( g_ev_fork, st ) != cudaSuccess || cudaStreamWaitEvent( g_aux, g_ev_fork, 0 ) != cudaSuccess ) return 0;
+   return g_aux;
+}
+// st continues after everything queued on the auxiliary stream
+int aux_join( cudaStream_t st )
+{
+   if( cudaEventRecord( g_ev_join, g_aux ) != cudaSuccess || cudaStreamWaitEvent( st, g_ev_join, 0 ) != cudaSuccess )
+      return set_error( "joining the auxiliary stream failed: %s", cudaGetErrorString( cudaGetLastError() ) );
+   return 0;
+}
 
 #define CUDA_OK( call )                                                                          \
    do                                                                                            \
@@ -317,6 +336,9 @@ int sw4b200_init( int device )
    int prio_lo = 0, prio_hi = 0;
    CUDA_OK( cudaDeviceGetStreamPriorityRange( &prio_lo, &prio_hi ) );
    for( int s = 0; s < 4; s++ ) CUDA_OK( cudaStreamCreateWithPriority( &g_streams[s], cudaStreamNonBlocking, s == 3 ? prio_hi : prio_lo ) );
+   CUDA_OK( cudaStreamCreateWithPriority( &g_aux, cudaStreamNonBlocking, prio_lo ) );
+   CUDA_OK( cudaEventCreateWithFlags( &g_ev_fork, cudaEventDisableTiming ) );
+   CUDA_OK( cudaEventCreateWithFlags( &g_ev_join, cudaEventDisableTiming ) );
    g_device = device;
    g_init = true;
    double acof[384], ghcof[6], bope[48], sbop[5];
@@ -330,6 +352,9 @@ int sw4b200_finalize( void )
    cudaDeviceSynchronize();
    for( int s = 0; s < 4; s++ )
       if( g_streams[s] ) { cudaStreamDestroy( g_streams[s] ); g_streams[s] = 0; }
+   if( g_aux ) { cudaStreamDestroy( g_aux ); g_aux = 0; }
+   if( g_ev_fork ) { cudaEventDestroy( g_ev_fork ); g_ev_fork = 0; }
+   if( g_ev_join ) { cudaEventDestroy( g_ev_join ); g_ev_join = 0; }
    free_scratch();
    g_init = false;
    g_device = -1;
@@ -1488,10 +1513,21 @@ int sw4b200_profile_reset( void )
 {
    prof_collect();
    g_prof_acc.clear();
-   return 0;
+   long long t[2];
+   return read_f4_tiles( t, true );
 }
 int sw4b200_profile_read( const char* kernel, double* ms_total, long long* launches )
 {
+   // thread blocks of the interior kernel by kind of tile (counted on the device whether or not the event timing is on)
+   if( kernel && ( !strcmp( kernel, "tiles_plain" ) || !strcmp( kernel, "tiles_general" ) ) )
+   {
+      long long t[2];
+      CUDA_OK( cudaDeviceSynchronize() );
+      if( read_f4_tiles( t, false ) ) return 1;
+      *ms_total = 0;
+      *launches = t[kernel[6] == 'p' ? 0 : 1];
+      return 0;
+   }
    prof_collect();
    auto it = g_prof_acc.find( kernel );
    *ms_total = it == g_prof_acc.end() ? 0.0 : it->second.first;

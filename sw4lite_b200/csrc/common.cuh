@@ -125,6 +125,8 @@ int launch_add_point_forces( int corder, long long npts, double* up, const doubl
 			     double* up2 = 0, double factor2 = 0, long long nij = 0, int kplane_lo = 0, int kplane_hi = 0 );
 int launch_gather_points( int corder, long long npts, const double* u, int n, const long long* pidx,
 			  double* out, cudaStream_t st );
+cudaStream_t aux_fork( cudaStream_t st ); // api.cu: the library's auxiliary stream, ordered after st (0: not available)
+int aux_join( cudaStream_t st );
 int launch_fill_profile( const Block& b, double* a, const double* prof, cudaStream_t st );
 int launch_derive_materials( long long n, const double* mu, const double* la, const double* rho, double* la2, double* rhoi, cudaStream_t st );
 int launch_halo_copy( const Block& b, double* field, int kplane, double* buf, int pack, cudaStream_t st );

@@ -37,6 +37,7 @@
 #include "fast_common.cuh"
 #include "tmem.cuh"
 #include "tma.cuh"
+#include <type_traits>
 
 namespace sw4b200 {
 
@@ -47,6 +48,23 @@ extern __shared__ __align__( 128 ) double smem_f4[];
 #define F4SM( c ) smem_f4
 #endif
 
+#if !defined( SW4B200_EMULATE )
+// thread blocks of k_rhs_fast4 that took the march without / with stretching factors (sw4b200_profile_read "tiles_plain",
+// "tiles_general"; one atomic per thread block)
+__device__ unsigned long long g_f4_tiles[2] = { 0, 0 };
+int read_f4_tiles( long long out[2], bool reset )
+{
+   unsigned long long v[2] = { 0, 0 };
+   if( cudaMemcpyFromSymbol( v, g_f4_tiles, sizeof( v ) ) != cudaSuccess ) return set_error( "reading the tile counters failed" );
+   out[0] = (long long)v[0]; out[1] = (long long)v[1];
+   if( reset )
+   {
+      const unsigned long long z[2] = { 0, 0 };
+      if( cudaMemcpyToSymbol( g_f4_tiles, z, sizeof( z ) ) != cudaSuccess ) return set_error( "resetting the tile counters failed" );
+   }
+   return 0;
+}
+#endif
 namespace fast4 {
 // DER (template parameter of the kernel): the staged "lambda" plane and the "rho" operand hold the derived, time-invariant
 // arrays 2 mu + lambda and 1 / rho of a grid block (FastArgs::la2, rhoi).  2 mu + lambda is then read instead of formed at
@@ -200,7 +218,10 @@ __device__ __forceinline__ double pick( const D2& v, int t ) { return t ? v.y : 
 // One step of the march: plane p has been staged into ring slot S.  Does the in-plane work of plane p,
 // the z work of plane k=p-2 (publishing its exchanged products in E buffer S&1) and finishes plane k-1
 // (reading E buffer (S+1)&1).
-template <int TY, int EPI, int SPLIT, bool DER, int H>
+// NOSTR: strx = 1 and stry = 1 on the whole tile (every tile away from the supergrid layers, nine tenths of a production grid):
+// the stretching factors are compile-time ones and their 22 multiplications per point disappear.  x * 1.0 and fma( x, 1.0, y )
+// are exact, so this body returns the bits of the general one.
+template <int TY, int EPI, int SPLIT, bool DER, bool NOSTR, int H>
 __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, Ctx<TY>& c, State& s, Tm& tm, const int p, const Ph& ph )
 {
    typedef Cfg<TY> C;
@@ -222,6 +243,14 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
 
    // strx at i-2..i+3 (i = left point), stry at j-2..j+2: re-read every step instead of held in 22 registers
    double csx[6], csy[5];
+   if( NOSTR )
+   {
+#pragma unroll
+      for( int j = 0; j < 6; j++ ) csx[j] = 1.0;
+#pragma unroll
+      for( int j = 0; j < 5; j++ ) csy[j] = 1.0;
+   }
+   else
    {
       const D2 s0 = ld2( F4SM( c ) + C::O_SX + 2 * c.txh ), s1 = ld2( F4SM( c ) + C::O_SX + 2 * c.txh + 2 ), s2 = ld2( F4SM( c ) + C::O_SX + 2 * c.txh + 4 );
       csx[0] = s0.x; csx[1] = s0.y; csx[2] = s1.x; csx[3] = s1.y; csx[4] = s2.x; csx[5] = s2.y;
@@ -449,7 +478,7 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
 	    const double hdzu = d0u( sf[0 * NSLOT * PLANE + ph.o[4] + oo], sf[0 * NSLOT * PLANE + ph.o[3] + oo],
 				     sf[0 * NSLOT * PLANE + ph.o[1] + oo], sf[0 * NSLOT * PLANE + ph.o[0] + oo] );
 	    double* const hx_ = F4SM( c ) + C::O_EX + EB * C::EX + ( sy_ - 2 ) * PX + sx_;
-	    hx_[0] = hl * ( F4SM( c )[C::O_SY + sy_] * hdyv + szk * hdzw );
+	    hx_[0] = hl * ( ( NOSTR ? 1.0 : F4SM( c )[C::O_SY + sy_] ) * hdyv + szk * hdzw );
 	    hx_[TY * PX] = hm * hdyu;
 	    hx_[2 * TY * PX] = ( hm * szk ) * hdzu;
 	 }
@@ -461,7 +490,7 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
 				     sf[1 * NSLOT * PLANE + ph.o[1] + oo], sf[1 * NSLOT * PLANE + ph.o[0] + oo] );
 	    double* const hy_ = F4SM( c ) + C::O_EY + EB * C::EY + sy_ * TX + ( sx_ - 2 );
 	    hy_[0] = hm * hdxv;
-	    hy_[PY * TX] = hl * ( F4SM( c )[C::O_SX + sx_] * hdxu + szk * hdzw );
+	    hy_[PY * TX] = hl * ( ( NOSTR ? 1.0 : F4SM( c )[C::O_SX + sx_] ) * hdxu + szk * hdzw );
 	    hy_[2 * PY * TX] = ( hm * szk ) * hdzv;
 	 }
       }
@@ -525,7 +554,12 @@ __device__ __forceinline__ void step( const FastArgs& a, const FastMaps& maps, C
 
 } // namespace fast4
 
-template <int TY, int EPI, int SPLIT, bool DER>
+// KIND: which tiles of the grid this launch serves -- 0: all, with the general march; 1: the plain tiles (strx = stry = 1 on
+// the whole tile), with the march compiled without stretching factors; 2: the other tiles, with the general march.  A thread
+// block of a tile of the other kind leaves at once.  The fused passes of a grid block are a launch of kind 2 followed by one
+// of kind 1 (two kernels rather than one with both marches: each keeps its own register allocation -- both marches in one
+// kernel cost the few spills that, with no L1 left beside 227 KB of shared memory, made the corrector pass 10 % slower).
+template <int TY, int EPI, int SPLIT, bool DER, int KIND>
 __global__ void __launch_bounds__( 16 * TY, 1 ) k_rhs_fast4( const FastArgs a, const SW4_GRID_CONSTANT FastMaps maps )
 {
    using namespace fast4;
@@ -550,6 +584,35 @@ __global__ void __launch_bounds__( 16 * TY, 1 ) k_rhs_fast4( const FastArgs a, c
    if( c.ka > c.kb ) return;
    c.pend = c.kb + 2;
 
+   bool plain = true; // no stretching on this tile: strx = stry = 1 at all its (in-array) points
+   for( int t = c.tid; t < PX + PY; t += NT )
+   {
+      if( t < PX )
+      {
+	 const int li = li0 - 2 + t;
+	 const double v = li < b.ni ? a.strx[li] : 0.0;
+	 smem[C::O_SX + t] = v;
+	 plain = plain && ( li >= b.nil || v == 1.0 ); // (nil: points per row; the pad column of a padded block does not count)
+      }
+      else
+      {
+	 const int lj = lj0 - 2 + ( t - PX );
+	 const double v = lj < b.nj ? a.stry[lj] : 0.0;
+	 smem[C::O_SY + t - PX] = v;
+	 plain = plain && ( lj >= b.nj || v == 1.0 );
+      }
+   }
+   if( KIND != 0 )
+   {
+      const bool nostr = __syncthreads_and( plain ) != 0;
+      if( nostr != ( KIND == 1 ) ) return; // a tile of the other launch
+#if defined( SW4B200_EMULATE )
+      if( KIND == 1 && c.tid == 0 ) emu::g_nostr_ctas++;
+#else
+      if( c.tid == 0 ) atomicAdd( &g_f4_tiles[KIND == 1 ? 0 : 1], 1ULL );
+#endif
+   }
+
    fast4::Tm tm;
    if( c.tid == 0 )
    {
@@ -570,19 +633,6 @@ __global__ void __launch_bounds__( 16 * TY, 1 ) k_rhs_fast4( const FastArgs a, c
    }
 #endif
 
-   for( int t = c.tid; t < PX + PY; t += NT )
-   {
-      if( t < PX )
-      {
-	 const int li = li0 - 2 + t;
-	 smem[C::O_SX + t] = li < b.ni ? a.strx[li] : 0.0;
-      }
-      else
-      {
-	 const int lj = lj0 - 2 + ( t - PX );
-	 smem[C::O_SY + t - PX] = lj < b.nj ? a.stry[lj] : 0.0;
-      }
-   }
    c.p0 = c.ka - 2;
    for( int t = c.tid; t <= c.kb + 3 - c.p0; t += NT )
    {
@@ -667,18 +717,19 @@ __global__ void __launch_bounds__( 16 * TY, 1 ) k_rhs_fast4( const FastArgs a, c
 	    s.amz[j][t] = s.amz[j + 2][t]; s.alz[j][t] = s.alz[j + 2][t];
 	 }
    };
+   constexpr bool NS = KIND == 1;
    int p = c.ka - 2;
    if( p & 1 )
    {
-      fast4::step<TY, EPI, SPLIT, DER, 1>( a, maps, c, s, tm, p, ph );
+      fast4::step<TY, EPI, SPLIT, DER, NS, 1>( a, maps, c, s, tm, p, ph );
       shift2(); next_plane(); p++;
    }
    while( p <= plast )
    {
-      fast4::step<TY, EPI, SPLIT, DER, 0>( a, maps, c, s, tm, p, ph );
+      fast4::step<TY, EPI, SPLIT, DER, NS, 0>( a, maps, c, s, tm, p, ph );
       next_plane(); p++;
       if( p > plast ) break;
-      fast4::step<TY, EPI, SPLIT, DER, 1>( a, maps, c, s, tm, p, ph );
+      fast4::step<TY, EPI, SPLIT, DER, NS, 1>( a, maps, c, s, tm, p, ph );
       shift2(); next_plane(); p++;
    }
 #if !defined( SW4B200_EMULATE )
@@ -691,7 +742,7 @@ __global__ void __launch_bounds__( 16 * TY, 1 ) k_rhs_fast4( const FastArgs a, c
 
 #ifndef SW4B200_EMULATE
 namespace {
-template <int TY, int EPI, int SPLIT, bool DER>
+template <int TY, int EPI, int SPLIT, bool DER, int KIND>
 int launch_fast4_t( FastArgs a, cudaStream_t st )
 {
    typedef fast4::Cfg<TY> C;
@@ -699,7 +750,7 @@ int launch_fast4_t( FastArgs a, cudaStream_t st )
    const size_t smem = C::SMEM_DOUBLES * sizeof( double );
    if( !configured )
    {
-      cudaError_t e = cudaFuncSetAttribute( k_rhs_fast4<TY, EPI, SPLIT, DER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem );
+      cudaError_t e = cudaFuncSetAttribute( k_rhs_fast4<TY, EPI, SPLIT, DER, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem );
       if( e != cudaSuccess ) return set_error( "k_rhs_fast4: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString( e ) );
       configured = true;
    }
@@ -719,14 +770,26 @@ int launch_fast4_t( FastArgs a, cudaStream_t st )
    }
    dim3 bs( C::NT, 1, 1 );
    dim3 gs( ( b.nil - 4 + C::TX - 1 ) / C::TX, ( b.nj - 4 + TY - 1 ) / TY, ( a.khi - a.klo + 1 + a.kchunk - 1 ) / a.kchunk );
-   ProfScope prof( EPI == EPI_PRED ? "rhs_fast_pred" : ( EPI == EPI_CORR ? "rhs_fast_corr" : "rhs_fast_lu" ), st );
-   k_rhs_fast4<TY, EPI, SPLIT, DER><<<gs, bs, smem, st>>>( a, maps );
+   k_rhs_fast4<TY, EPI, SPLIT, DER, KIND><<<gs, bs, smem, st>>>( a, maps );
    count_launch();
    return check_launch( "k_rhs_fast4" );
 }
 } // namespace
 
 int launch_fast2( int epi, FastArgs a, cudaStream_t st );
+
+namespace {
+// the two launches of a fused pass (plain tiles, tiles with stretching: disjoint outputs, read-only inputs): the second on the
+// auxiliary stream, so that its thread blocks fill the SMs the first leaves idle in its last wave instead of adding a tail
+int launch_pair( int ( *plain )( FastArgs, cudaStream_t ), int ( *general )( FastArgs, cudaStream_t ), const FastArgs& a, cudaStream_t st )
+{
+   cudaStream_t aux = aux_fork( st );
+   if( plain( a, st ) ) return 1;
+   if( !aux ) return general( a, st );
+   const int rc = general( a, aux );
+   return aux_join( st ) || rc;
+}
+} // namespace
 
 int launch_fast4( int epi, const FastArgs& a, cudaStream_t st )
 {
@@ -747,19 +810,21 @@ int launch_fast4( int epi, const FastArgs& a, cudaStream_t st )
    // the fused passes of this kernel exist for the derived coefficient arrays of a grid block only
    if( epi != EPI_LU && ( !a.la2 || !a.rhoi ) ) return launch_fast2( epi, a, st );
    // grid blocks with an odd number of points per row are allocated with rows padded to an even pitch (api.cu): the last pair of
-   // a row is then split by the boundary (SPLIT variant: that pair stores its left point only)
+   // a row is then split by the boundary (SPLIT variant: that pair stores its left point only).
+   // The fused passes: the plain tiles and, beside them, the tiles with stretching (see KIND above)
+   ProfScope prof( epi == EPI_PRED ? "rhs_fast_pred" : ( epi == EPI_CORR ? "rhs_fast_corr" : "rhs_fast_lu" ), st );
    if( a.b.nil != a.b.ni )
       switch( epi )
       {
-      case EPI_LU: return launch_fast4_t<16, EPI_LU, 1, false>( a, st );
-      case EPI_PRED: return launch_fast4_t<16, EPI_PRED, 1, true>( a, st );
-      default: return launch_fast4_t<16, EPI_CORR, 1, true>( a, st );
+      case EPI_LU: return launch_fast4_t<16, EPI_LU, 1, false, 0>( a, st );
+      case EPI_PRED: return launch_pair( launch_fast4_t<16, EPI_PRED, 1, true, 1>, launch_fast4_t<16, EPI_PRED, 1, true, 2>, a, st );
+      default: return launch_pair( launch_fast4_t<16, EPI_CORR, 1, true, 1>, launch_fast4_t<16, EPI_CORR, 1, true, 2>, a, st );
       }
    switch( epi )
    {
-   case EPI_LU: return launch_fast4_t<16, EPI_LU, 0, false>( a, st );
-   case EPI_PRED: return launch_fast4_t<16, EPI_PRED, 0, true>( a, st );
-   default: return launch_fast4_t<16, EPI_CORR, 0, true>( a, st );
+   case EPI_LU: return launch_fast4_t<16, EPI_LU, 0, false, 0>( a, st );
+   case EPI_PRED: return launch_pair( launch_fast4_t<16, EPI_PRED, 0, true, 1>, launch_fast4_t<16, EPI_PRED, 0, true, 2>, a, st );
+   default: return launch_pair( launch_fast4_t<16, EPI_CORR, 0, true, 1>, launch_fast4_t<16, EPI_CORR, 0, true, 2>, a, st );
    }
 }
 #endif

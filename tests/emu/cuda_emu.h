@@ -6,6 +6,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <cmath>
+#include <atomic>
 #include <barrier>
 #include <thread>
 #include <vector>
@@ -33,6 +34,18 @@ extern std::barrier<>* g_barrier;
 #define blockDim ( emu::g_blockDim )
 #define gridDim ( emu::g_gridDim )
 inline void __syncthreads() { emu::g_barrier->arrive_and_wait(); }
+// block-wide AND of a predicate (threads that have left the block do not vote)
+namespace emu { extern std::atomic<int> g_vote_false; extern int g_force_general, g_nostr_ctas; }
+inline int __syncthreads_and( int pred )
+{
+   if( !pred ) emu::g_vote_false.fetch_add( 1 );
+   emu::g_barrier->arrive_and_wait();
+   const int r = emu::g_vote_false.load() == 0;
+   emu::g_barrier->arrive_and_wait();
+   if( threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0 ) emu::g_vote_false.store( 0 );
+   emu::g_barrier->arrive_and_wait();
+   return r;
+}
 inline double* emu_shared_memory() { return emu::g_smem; }
 
 namespace emu {

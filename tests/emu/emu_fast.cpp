@@ -6,11 +6,33 @@ thread_local dim3 t_threadIdx;
 dim3 g_blockIdx, g_blockDim, g_gridDim;
 double* g_smem = 0;
 std::barrier<>* g_barrier = 0;
+std::atomic<int> g_vote_false( 0 );
+int g_force_general = 0, g_nostr_ctas = 0;
 }
+extern "C" int emu_nostr_ctas() { const int n = emu::g_nostr_ctas; emu::g_nostr_ctas = 0; return n; }
+extern "C" void emu_force_general( int on ) { emu::g_force_general = on; }
 #include "../../sw4lite_b200/csrc/rhs4sg_fast2.cu"
 #include "../../sw4lite_b200/csrc/rhs4sg_fast4.cu"
 
 using namespace sw4b200;
+
+// what launch_fast4 does: the Lu epilogue in one launch of all tiles (KIND 0); the fused passes as a launch of the tiles with
+// stretching (KIND 2) and one of the plain tiles (KIND 1) -- or, with the test hook emu_force_general, as ONE launch of all
+// tiles with the general march, for the bit comparison of the two marches
+#define EMU_FAST4_K( EPI_, SPLIT_, DER_, KIND_ ) \
+   emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_, SPLIT_, DER_, KIND_>( a, maps ); } )
+#define EMU_FAST4( SPLIT_ )                                                                             \
+   if( epi == EPI_LU ) EMU_FAST4_K( EPI_LU, SPLIT_, false, 0 );                                          \
+   else if( epi == EPI_PRED )                                                                            \
+   {                                                                                                     \
+      if( emu::g_force_general ) EMU_FAST4_K( EPI_PRED, SPLIT_, true, 0 );                               \
+      else { EMU_FAST4_K( EPI_PRED, SPLIT_, true, 2 ); EMU_FAST4_K( EPI_PRED, SPLIT_, true, 1 ); }       \
+   }                                                                                                     \
+   else                                                                                                  \
+   {                                                                                                     \
+      if( emu::g_force_general ) EMU_FAST4_K( EPI_CORR, SPLIT_, true, 0 );                               \
+      else { EMU_FAST4_K( EPI_CORR, SPLIT_, true, 2 ); EMU_FAST4_K( EPI_CORR, SPLIT_, true, 1 ); }       \
+   }
 
 // gen 4: rhs4sg_fast4.cu (the product configuration; the SPLIT variant when pitch > ni), gen 2: rhs4sg_fast2.cu.
 // pitch = row pitch of the arrays in doubles (ni, or ni+1 for a block whose odd rows are padded to an even pitch)
@@ -53,15 +75,11 @@ extern "C" int emu_rhs_fast( int gen, int epi, int ifirst, int ilast, int jfirst
       maps.mu.base = a.mu; maps.la.base = epi != EPI_LU ? a.la2 : a.la; maps.rho.base = epi != EPI_LU ? a.rhoi : a.rho;
       if( a.b.nil == a.b.ni )
       {
-	 if( epi == EPI_LU ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_LU, 0, false>( a, maps ); } );
-	 else if( epi == EPI_PRED ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_PRED, 0, true>( a, maps ); } );
-	 else emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_CORR, 0, true>( a, maps ); } );
+	 EMU_FAST4( 0 )
       }
       else
       {
-	 if( epi == EPI_LU ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_LU, 1, false>( a, maps ); } );
-	 else if( epi == EPI_PRED ) emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_PRED, 1, true>( a, maps ); } );
-	 else emu::launch( gs, bs, C4::SMEM_DOUBLES, [&]() { k_rhs_fast4<TY4, EPI_CORR, 1, true>( a, maps ); } );
+	 EMU_FAST4( 1 )
       }
       return 0;
    }

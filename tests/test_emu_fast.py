@@ -43,6 +43,7 @@ def emu():
     lib = C.CDLL(LIB)
     lib.emu_rhs_fast.argtypes = [C.c_int] * 12 + [_dp] * 6 + [C.c_double] + [_dp] * 5 + [C.c_double]
     lib.emu_rhs_fast.restype = C.c_int
+    lib.emu_force_general.argtypes = [C.c_int]
     return lib
 
 
@@ -164,3 +165,50 @@ def test_emu_predictor_and_corrector_epilogues(emu):
     out = f["up"].copy()
     run(emu, 2, box, box.kfirst + 2, box.klast - 2, 6, f, 1 / h ** 2, out, um=out, rho=f["rho"], fo=None if GEN in (4, 40) else f["fo"], fac=dt ** 4 / 12)
     assert relerr(r4(out)[inner], r4(ref)[inner]) < 1e-13
+
+
+@pytest.mark.parametrize("epi", [0, 1, 2])
+def test_emu_plain_tiles_take_the_body_without_stretching(emu, epi):
+    """tiles on which strx = stry = 1 run the march compiled without the stretching factors (rhs4sg_fast4.cu, NOSTR):
+    equal to the oracle and bit-identical to the general body on the same tiles; here 2 x 2 tiles of which the
+    first column and the first row are stretched (a supergrid layer) and one tile is plain"""
+    if GEN == 2:
+        pytest.skip("rhs4sg_fast4.cu only")
+    box = Box(*even((60, 30, 14)))
+    f = random_fields(box, seed=31)
+    f["strx"][10:] = 1.0
+    f["stry"][9:] = 1.0
+    f["fo"] = np.zeros_like(f["fo"])
+    h, dt = 0.6, 0.04
+    lu = cpu_lu(box, f, h)
+    O = oracle()
+    if epi == 0:
+        ref = lu
+    elif epi == 1:
+        ref = np.zeros(3 * box.npts)
+        O.predfort(1, box.bounds, ref, f["u"], f["um"], lu, f["fo"], f["rho"], dt * dt)
+    else:
+        ref = f["up"].copy()
+        O.corrfort(1, box.bounds, ref, lu, f["fo"], f["rho"], dt ** 4)
+    res = []
+    try:
+        for force in (0, 1):
+            emu.emu_force_general(force)
+            emu.emu_nostr_ctas()
+            out = f["up"].copy() if epi == 2 else np.zeros(3 * box.npts)
+            out2 = np.zeros(3 * box.npts) if epi == 1 else None
+            run(emu, epi, box, box.kfirst + 2, box.klast - 2, 7, f, 1 / h ** 2, out, out2=out2,
+                um=out if epi == 2 else (f["um"] if epi == 1 else None), rho=f["rho"] if epi else None,
+                fac=(dt * dt if epi == 1 else dt ** 4 / 12))
+            res.append((out, out2))
+            # one of the 2 x 2 tiles is plain; 10 interior planes in chunks of 7 -> 2 CTAs per tile
+            # (the Lu epilogue is one launch of all tiles with the general march)
+            assert emu.emu_nostr_ctas() == (0 if force or epi == 0 else 2)
+    finally:
+        emu.emu_force_general(0)
+    inner = (slice(None), slice(2, -2), slice(2, -2), slice(2, -2))
+    r4 = lambda x: x.reshape(3, box.nk, box.nj, box.ni)
+    assert relerr(r4(res[0][0])[inner], r4(ref)[inner]) < 1e-13
+    assert np.array_equal(res[0][0], res[1][0])
+    if epi == 1:
+        assert np.array_equal(res[0][1], res[1][1])
