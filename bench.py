@@ -487,10 +487,11 @@ def main_ours(a):
                 "algorithmic_bytes_per_point": BYTES_PASS_A, "points_per_launch": a.nx * a.ny * rows,
                 "ms_per_launch": dur, "step_frac_of_hbm": BYTES_PER_POINT_STEP * gpts / N / peak}
         # the co-bound: fp64 pipe.  Measured FMA rate of this GPU (register-only chain kernel) against the kernel's fp64
-        # instruction count per point (ncu: DADD+DMUL+DFMA = 261 warp-instructions per 32 points, profiles/r01d)
+        # instruction count per point (ncu source page, thread instructions DADD+DMUL+DFMA / points: 244 with the derived
+        # coefficient arrays and the march without stretching factors on the plain tiles, profiles/r02y; round 1: 261)
         tf, fr = C.c_double(0), C.c_double(0)
         if lib.sw4b200_measure_fp64_peak(C.byref(tf), C.byref(fr)) == 0 and fr.value > 0:
-            FP64_INSTR_PER_POINT = 261.0
+            FP64_INSTR_PER_POINT = 244.0
             roof["fp64_cobound"] = {"measured_fma_tflops": tf.value, "kernel_fp64_instr_per_point": FP64_INSTR_PER_POINT,
                                     "pipe_frac": FP64_INSTR_PER_POINT * a.nx * a.ny * rows / prof["rhs_fast_pred"]["launches_per_step"] / (dur * 1e-3) / fr.value,
                                     "pass_floor_ms": 1e3 * FP64_INSTR_PER_POINT * a.nx * a.ny * rows / prof["rhs_fast_pred"]["launches_per_step"] / fr.value,
