@@ -37,6 +37,9 @@
 #include "fast_common.cuh"
 #include "tmem.cuh"
 #include "tma.cuh"
+#ifndef SW4B200_EMULATE
+#include <mutex>
+#endif
 #include <type_traits>
 
 namespace sw4b200 {
@@ -783,6 +786,9 @@ namespace {
 // auxiliary stream, so that its thread blocks fill the SMs the first leaves idle in its last wave instead of adding a tail
 int launch_pair( int ( *plain )( FastArgs, cudaStream_t ), int ( *general )( FastArgs, cudaStream_t ), const FastArgs& a, cudaStream_t st )
 {
+   // (the library has ONE auxiliary stream and one pair of fork / join events: host threads driving different grids take turns)
+   static std::mutex mtx;
+   std::lock_guard<std::mutex> lock( mtx );
    cudaStream_t aux = aux_fork( st );
    if( plain( a, st ) ) return 1;
    if( !aux ) return general( a, st );

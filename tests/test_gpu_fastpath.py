@@ -115,6 +115,46 @@ def test_bench_kernels_step_matches_oracle(shape):
     print("shape %s pitch %d: worst per-step rel. diff %.3g, launches %s" % (shape, pitch, worst, n))
 
 
+def tile_counters(lib):
+    out = []
+    for n in ("tiles_plain", "tiles_general"):
+        tot = C.c_double(0); cnt = C.c_longlong(0)
+        lib.sw4b200_profile_read(n.encode(), C.byref(tot), C.byref(cnt))
+        out.append(int(cnt.value))
+    return out
+
+
+@pytest.mark.parametrize("shape", [(140, 70, 30), (139, 70, 30)], ids=["even-ni", "odd-ni"])
+def test_plain_tiles_and_stretched_tiles_match_oracle(shape):
+    """a grid wide enough for tiles away from the supergrid layers (strx = stry = 1 on the whole tile): those take the kernel
+    compiled without stretching factors (KIND 1), the tiles in the layers the general one (KIND 2), side by side on two
+    streams; every step against the oracle, and both kinds of thread block did run.  After two steps the density is changed
+    through sw4b200_grid_upload: the block's derived arrays (1 / rho, 2 mu + lambda) must follow"""
+    import sw4lite_b200 as S
+    from tests.cpu_step import OracleStepper
+    lib = S.init(0)
+    prob = problem(*shape)
+    with counting(lib) as c:
+        blk, cpu, worst = step_both(prob, 3)
+        plain, general = tile_counters(lib)
+    assert c.n["rhs_fast_pred"] >= 3 and c.n["rhs_fast2_pred"] == 0 and c.n["rhs_v1"] == 0, c.n
+    # 5 x 5 tiles of 32 x 16 (the inner ones plain) x k-chunks, 2 passes x 3 steps: every thread block ran in exactly one launch
+    assert plain > 0 and general > 0 and (plain + general) % (6 * 5 * 5) == 0, (plain, general)
+    # material update after the first steps
+    rho = blk.download("rho") * 1.25
+    mu = blk.download("mu") * 0.9
+    blk.upload("rho", rho); blk.upload("mu", mu)
+    cpu.rho[:] = rho; cpu.mu[:] = mu
+    t = 3 * prob.dt
+    for step in range(2):
+        f, ftt = prob.forces(t), prob.forces(t, tt=True)
+        blk.step(f, ftt); cpu.step(f, ftt)
+        t += prob.dt
+        e = relerr(blk.download("U"), cpu.U)
+        assert e < TOL, "step %d after the material update differs from the oracle: %.3g" % (step + 1, e)
+    print("shape %s: worst per-step rel. diff %.3g, thread blocks plain / general %d / %d" % (shape, worst, plain, general))
+
+
 def test_both_closures_on_the_tma_kernels():
     """stress-free surfaces on top AND bottom: SBP closure rows 1..6 and nz-5..nz (rhs4sg_rev.C:349-855)"""
     import sw4lite_b200 as S
